@@ -1,0 +1,139 @@
+/* rmx.h — C ABI of the B200-native radio-mapper hot path (librmx.so).
+ *
+ * The reference (physiii/radio-mapper) has NO native/FFI boundary for this path: its
+ * arithmetic is in-process numpy/scipy calls inside Python modules.  Each entry point below
+ * therefore cites the reference *Python* lines whose arithmetic it replaces; the host-side
+ * drop-in (radio_mapper_b200/tdoa_processor.py, signal_analyzer.py, detectors.py) keeps the
+ * reference's class / function signatures and calls these through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory unless the name says host;
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it;
+ *   - return 0 on success, negative on error; `rmx_last_error()` returns the thread-local text;
+ *   - the library allocates device memory only inside a plan (twiddle tables, window);
+ *   - no exceptions cross the boundary; no torch types appear in signatures.
+ *
+ * Spectrum layout: `rmx_fft_forward_cu8` writes spectra in the plan's "digit-transposed" order
+ * (see rmx_plan_layout); `rmx_xcorr_pairs_peak` consumes that order; `rmx_spectrum_db` and
+ * `rmx_spectrum_natural` convert to natural bin order for anything that needs it.
+ */
+#ifndef RMX_H_
+#define RMX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMX_VERSION 100
+
+#if defined(__GNUC__)
+#define RMX_API __attribute__((visibility("default")))
+#else
+#define RMX_API
+#endif
+
+typedef struct rmx_plan rmx_plan;
+
+/* per-pair result of the lag search (16 bytes) */
+typedef struct rmx_peak {
+    int32_t lag;   /* integer lag of max |c|, samples; >0: signal j arrived later (tdoa_processor.py:51) */
+    float peak;    /* |c[lag]|, unnormalised like scipy.signal.correlate */
+    float frac;    /* parabolic vertex offset in (-0.5, 0.5), 0 at the range edge */
+    float pad;     /* |c|^2 found by the tile search (diagnostic) */
+} rmx_peak;
+
+typedef struct rmx_complex64 { float re, im; } rmx_complex64;
+typedef struct rmx_pair { int32_t i, j; } rmx_pair;      /* signal indices, i != j */
+
+/* signal statistics (signal_analyzer.py:92-99) */
+typedef struct rmx_stats {
+    double mean_power;     /* mean |x|^2 (exact integer arithmetic on the cu8 samples) */
+    float peak_amplitude;  /* max |x| */
+    float pad;
+} rmx_stats;
+
+enum {
+    RMX_OK = 0,
+    RMX_ERR_ARG = -1,        /* bad argument */
+    RMX_ERR_UNSUPPORTED = -2,/* size not supported by the kernels */
+    RMX_ERR_CUDA = -3,       /* CUDA runtime error (text in rmx_last_error) */
+    RMX_ERR_WORKSPACE = -4   /* workspace too small */
+};
+
+RMX_API const char* rmx_last_error(void);
+RMX_API int rmx_version(void);
+
+/* Stage 1 — cu8 unpack:  out[n] = (in[2n]-127.5) + i*(in[2n+1]-127.5)   (bit-exact)
+ * replaces buoy_node.py:392-398, iq_stream_client.py:149-157, signal_analyzer.py:28-36 */
+RMX_API int rmx_unpack_cu8(const uint8_t* in, rmx_complex64* out, size_t n_samples, void* stream);
+
+/* Plan: n_signals signals of n_samples complex samples each, zero-padded to fft_len (a power of
+ * two >= 16, >= n_samples).  flags: reserved (0). */
+RMX_API int rmx_plan_create(rmx_plan** plan, int n_signals, size_t n_samples, size_t fft_len, unsigned flags);
+RMX_API int rmx_plan_destroy(rmx_plan* plan);
+/* number of passes and their lengths n_t (outermost first); returns n_passes */
+RMX_API int rmx_plan_layout(const rmx_plan* plan, int32_t* pass_lengths, int cap);
+/* bytes of workspace needed to correlate `n_pairs` pairs in one chunk */
+RMX_API size_t rmx_plan_workspace_bytes(const rmx_plan* plan, int n_pairs);
+/* restrict the lag search to [-max_lag, +max_lag]; max_lag < 0 restores the full range
+ * -(n_samples-1) .. n_samples-1 of scipy.signal.correlate(mode='full') */
+RMX_API int rmx_plan_set_max_lag(rmx_plan* plan, long long max_lag);
+
+/* Stages 1+2 — fused unpack + zero-pad + batched forward FFT of all signals.
+ * iq: uint8[n_signals][2*n_samples]; spectra: complex64[n_signals][fft_len] (plan layout).
+ * replaces fft(iq_samples) of buoy_node.py:401 / iq_stream_client.py:187 / signal_analyzer.py:63 */
+RMX_API int rmx_fft_forward_cu8(const rmx_plan* plan, const uint8_t* iq, rmx_complex64* spectra, void* stream);
+
+/* plan layout -> natural bin order (out may not alias in) */
+RMX_API int rmx_spectrum_natural(const rmx_plan* plan, const rmx_complex64* spectra, rmx_complex64* out,
+                         int n_signals, void* stream);
+
+/* Stages 3+4 — for every pair (i, j): c = ifft(X_j * conj(X_i)) == scipy.signal.correlate(x_j, x_i,
+ * 'full', 'fft'); arg-max of |c| over the lag range, 3-point parabolic vertex.  One launch per
+ * pass covers all pairs of a chunk.  pairs: device rmx_pair[n_pairs]; out: device rmx_peak[n_pairs].
+ * (absent in the reference — tdoa_processor.py:20 imports correlate but only subtracts timestamps,
+ * :166; this produces the time difference that line computes) */
+RMX_API int rmx_xcorr_pairs_peak(const rmx_plan* plan, const rmx_complex64* spectra, const rmx_pair* pairs,
+                         int n_pairs, rmx_peak* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stage 5a — dB spectrum in natural order: out[k] = 20*log10(|X[k]| + 1e-12); shift != 0 applies
+ * fftshift.  replaces buoy_node.py:405, iq_stream_client.py:191, signal_analyzer.py:64-67 */
+RMX_API int rmx_spectrum_db(const rmx_plan* plan, const rmx_complex64* spectra, float* out_db, int n_signals,
+                    int shift, void* stream);
+
+/* Stage 5b — Welch PSD (Hann, no overlap, no detrend, two-sided, density scaling): the plan's
+ * n_signals are the segments, n_samples == fft_len == nperseg.  psd: float[fft_len], natural order.
+ * == scipy.signal.welch(x, fs, 'hann', nperseg, 0, detrend=False, return_onesided=False) */
+RMX_API int rmx_welch_psd(rmx_plan* plan, const uint8_t* iq, float* psd, double sample_rate,
+                  void* workspace, size_t workspace_bytes, void* stream);
+RMX_API size_t rmx_welch_workspace_bytes(const rmx_plan* plan, int segments_in_flight);
+
+/* out[k] = 10*log10(in[k] + eps) */
+RMX_API int rmx_power_db(const float* in, float* out, size_t n, float eps, void* stream);
+
+/* Stage 5c — peak candidates: scipy's _local_maxima_1d (plateau midpoints, end points excluded)
+ * with db[k] >= height, compacted in unspecified order into idx[0..min(count,cap)).
+ * replaces the first two stages of find_peaks (buoy_node.py:411-415, signal_analyzer.py:75) */
+RMX_API int rmx_threshold_peaks(const float* db, int n, float height, int32_t* idx, int32_t* count, int cap,
+                        void* stream);
+
+/* HOST helper: find_peaks' greedy minimum-distance rule on sorted candidate positions.
+ * keep[i] = 1 if candidate i survives.  All pointers are host pointers. */
+RMX_API int rmx_select_by_distance_host(const int32_t* positions, const float* heights, int n, int distance,
+                                uint8_t* keep);
+
+/* mean(db) (double accumulation) and median(db) (np.median: mean of the two middle order
+ * statistics for even n).  out: device float[2] = {mean, median}.  workspace: >= 4 KiB.
+ * replaces np.mean(...) signal_analyzer.py:75 and np.median(...) buoy_node.py:427 */
+RMX_API int rmx_mean_median(const float* db, int n, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* signal statistics straight from cu8 (signal_analyzer.py:92-99); out: device rmx_stats */
+RMX_API int rmx_signal_stats(const uint8_t* iq, size_t n_samples, rmx_stats* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMX_H_ */

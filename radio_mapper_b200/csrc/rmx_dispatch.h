@@ -1,0 +1,23 @@
+// rmx_dispatch.h — lookup of the template-instantiated pass kernels (internal).
+#pragma once
+#include "rmx_kernels.cuh"
+
+namespace rmx {
+
+typedef void (*PassKernel)(const PassParams);
+
+struct KernelEntry {
+    PassKernel fn;      // nullptr if this (logn, loge, mode) is not instantiated
+    size_t smem_bytes;  // dynamic shared memory
+    int logG;           // log2(FFTs per tile)
+};
+
+KernelEntry get_contig_kernel(int logn, int loge, int mode);
+KernelEntry get_col_kernel(int logn, int loge, int mode);
+
+// supported ranges for register tile size 2^loge
+inline int max_contig_logn(int loge) { return kLogThreads + loge; }
+inline int max_col_logn(int loge) { return kLogThreads + loge - 3; }   // >= 8 columns per tile
+inline int min_logn(int loge) { return loge; }
+
+}  // namespace rmx

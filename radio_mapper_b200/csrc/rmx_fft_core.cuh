@@ -1,0 +1,281 @@
+// rmx_fft_core.cuh — register/shared-memory FFT building blocks for sm_100a.
+//
+// One CTA (256 threads) transforms one TILE of 256*E complex points held E-per-thread in
+// registers.  A tile is G independent FFTs of length n (n*G == TILE).  Each FFT is a
+// Stockham autosort pipeline of radix-E register DFTs; between stages the tile is
+// exchanged through padded shared memory (conflict-free for 64-bit accesses).  The first
+// stage loads straight from global memory into registers and the last stage stores
+// straight from registers, so shared memory carries only the inter-stage exchanges.
+//
+// Thread <-> data map (both first-stage loads and last-stage stores):
+//      thread (g, i0) holds rows  i0 + u*(n/E),  u = 0..E-1   of FFT g.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <type_traits>
+
+namespace rmx {
+
+constexpr int kThreads = 256;
+constexpr int kLogThreads = 8;
+constexpr int kMaxStages = 4;
+
+// ---------------------------------------------------------------------------------------
+// small complex helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ float cnorm2(float2 a) { return a.x * a.x + a.y * a.y; }
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+__host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr int bitrev(int v, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+__host__ __device__ constexpr int ilog2(int v) {
+    int r = 0;
+    while ((1 << r) < v) ++r;
+    return r;
+}
+
+// cos/sin(2*pi*k/32), k = 0..31, correctly rounded to float.
+constexpr float kCos32[32] = {
+    1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+    0.70710678118654757f, 0.55557023301960218f, 0.38268343236508978f, 0.19509032201612825f,
+    0.0f, -0.19509032201612825f, -0.38268343236508978f, -0.55557023301960218f,
+    -0.70710678118654757f, -0.83146961230254524f, -0.92387953251128674f, -0.98078528040323043f,
+    -1.0f, -0.98078528040323043f, -0.92387953251128674f, -0.83146961230254524f,
+    -0.70710678118654757f, -0.55557023301960218f, -0.38268343236508978f, -0.19509032201612825f,
+    0.0f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
+    0.70710678118654757f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f};
+constexpr float kSin32[32] = {
+    0.0f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
+    0.70710678118654757f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f,
+    1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+    0.70710678118654757f, 0.55557023301960218f, 0.38268343236508978f, 0.19509032201612825f,
+    0.0f, -0.19509032201612825f, -0.38268343236508978f, -0.55557023301960218f,
+    -0.70710678118654757f, -0.83146961230254524f, -0.92387953251128674f, -0.98078528040323043f,
+    -1.0f, -0.98078528040323043f, -0.92387953251128674f, -0.83146961230254524f,
+    -0.70710678118654757f, -0.55557023301960218f, -0.38268343236508978f, -0.19509032201612825f};
+
+// a * exp(-2*pi*i*EXP/32)   (forward twiddle; the inverse uses EXP -> 32-EXP)
+template <int EXP>
+__device__ __forceinline__ float2 mul_w32_fwd(float2 a) {
+    constexpr int e = EXP & 31;
+    constexpr float h = 0.70710678118654757f;
+    if constexpr (e == 0) return a;
+    else if constexpr (e == 8) return make_float2(a.y, -a.x);
+    else if constexpr (e == 16) return make_float2(-a.x, -a.y);
+    else if constexpr (e == 24) return make_float2(-a.y, a.x);
+    else if constexpr (e == 4) return make_float2(h * (a.x + a.y), h * (a.y - a.x));
+    else if constexpr (e == 12) return make_float2(h * (a.y - a.x), -h * (a.x + a.y));
+    else if constexpr (e == 20) return make_float2(-h * (a.x + a.y), h * (a.x - a.y));
+    else if constexpr (e == 28) return make_float2(h * (a.x - a.y), h * (a.x + a.y));
+    else {
+        constexpr float c = kCos32[e], s = kSin32[e];
+        return make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+    }
+}
+template <int EXP, bool INV>
+__device__ __forceinline__ float2 mul_w32(float2 a) {
+    return mul_w32_fwd<INV ? (32 - (EXP & 31)) & 31 : (EXP & 31)>(a);
+}
+
+// One radix-2 DIF layer over sub-transforms of length LEN inside an R-point register DFT.
+template <int R, int LEN, bool INV>
+__device__ __forceinline__ void dif_layers(float2 (&x)[R]) {
+    constexpr int half = LEN / 2;
+    static_for<0, R / 2>([&](auto I) {
+        constexpr int idx = decltype(I)::value;
+        constexpr int blk = idx / half, k = idx % half;
+        constexpr int a = blk * LEN + k, b = a + half;
+        const float2 u = x[a], v = x[b];
+        x[a] = cadd(u, v);
+        x[b] = mul_w32<(32 / LEN) * k, INV>(csub(u, v));
+    });
+    if constexpr (LEN > 2) dif_layers<R, LEN / 2, INV>(x);
+}
+
+// R-point DFT (R = 2..32) of a register array, natural order in and out.
+template <int R, bool INV>
+__device__ __forceinline__ void dft_regs(float2 (&x)[R]) {
+    if constexpr (R > 1) {
+        dif_layers<R, R, INV>(x);
+        float2 t[R];
+        static_for<0, R>([&](auto I) { constexpr int q = decltype(I)::value; t[q] = x[bitrev(q, ilog2(R))]; });
+        static_for<0, R>([&](auto I) { constexpr int q = decltype(I)::value; x[q] = t[q]; });
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// tile geometry
+// ---------------------------------------------------------------------------------------
+template <int LOGN_, int LOGE_, bool COLUMN_>
+struct TileGeom {
+    static constexpr int LOGN = LOGN_, LOGE = LOGE_;
+    static constexpr bool COLUMN = COLUMN_;
+    static constexpr int E = 1 << LOGE;
+    static constexpr int N = 1 << LOGN;
+    static constexpr int LOGTILE = kLogThreads + LOGE;
+    static constexpr int TILE = 1 << LOGTILE;
+    static_assert(LOGN <= LOGTILE, "FFT longer than a tile");
+    static constexpr int LOGG = LOGTILE - LOGN;          // FFTs per tile
+    static constexpr int G = 1 << LOGG;
+    static constexpr int LOGNT = cmax(LOGN - LOGE, 0);   // threads per FFT
+    static constexpr int NT = 1 << LOGNT;
+    static constexpr int ROWSTEP = NT;                   // rows held by a thread: i0 + u*ROWSTEP
+    static constexpr int NSTAGES = (LOGN + LOGE - 1) / LOGE;
+    static constexpr int LOGR0 = cmin(LOGE, LOGN);
+    static constexpr int NP = N + (N >> LOGR0);          // padded FFT length
+    static constexpr size_t SMEM_BYTES = NSTAGES > 1 ? size_t(NP) * G * sizeof(float2) : 0;
+    static_assert(LOGN >= LOGE, "FFT shorter than a thread's register tile is not supported");
+
+    __device__ static __forceinline__ int stage_logr(int s) { return cmin(LOGE, LOGN - s * LOGE); }
+    // shared-memory element index of (fft g, position pos)
+    __device__ static __forceinline__ int saddr(int g, int pos) {
+        const int pp = pos + (pos >> LOGR0);
+        if constexpr (COLUMN) return (pp << LOGG) + g;
+        else return g * NP + pp;
+    }
+    // thread -> (fft g, first row i0)
+    __device__ static __forceinline__ void thread_map(int v, int& g, int& i0) {
+        if constexpr (COLUMN) { g = v & (G - 1); i0 = v >> LOGG; }
+        else { i0 = v & (NT - 1); g = v >> LOGNT; }
+    }
+};
+
+struct StageTables {
+    // tw[s] : table for stage s (s >= 1), entries [(q-1)*p + k] = exp(-2*pi*i*q*k/(p*R)), q=1..R-1, k<p
+    const float2* tw[kMaxStages];
+};
+
+// Run all Stockham stages on the register tile.  On entry r[u] = x[i0 + u*NT]; on exit
+// r[u] = X[i0 + u*NT] (natural order).  All 256 threads must call (contains barriers).
+template <class GEO, bool INV>
+__device__ __forceinline__ void fft_tile(float2 (&r)[GEO::E], float2* smem, int g, int i0, const StageTables& tabs) {
+    constexpr int E = GEO::E, LOGE = GEO::LOGE, LOGN = GEO::LOGN, NT = GEO::NT;
+    static_for<0, GEO::NSTAGES>([&](auto S_) {
+        constexpr int S = decltype(S_)::value;
+        constexpr int LOGP = S * LOGE;
+        constexpr int LOGR = cmin(LOGE, LOGN - LOGP);
+        constexpr int R = 1 << LOGR;
+        constexpr int NB = E / R;                 // butterflies per thread in this stage
+        constexpr int T = 1 << (LOGN - LOGR);     // butterflies per FFT in this stage
+        constexpr int P = 1 << LOGP;
+        if constexpr (S > 0) {
+            // gather this stage's inputs: x[i + q*T]
+            static_for<0, NB>([&](auto B_) {
+                constexpr int b = decltype(B_)::value;
+                const int i = i0 + b * NT;
+                static_for<0, R>([&](auto Q_) {
+                    constexpr int q = decltype(Q_)::value;
+                    r[b + q * NB] = smem[GEO::saddr(g, i + q * T)];
+                });
+            });
+            // twiddle by w_{P*R}^{q*k}, k = i mod P
+            const float2* __restrict__ tw = tabs.tw[S];
+            static_for<0, NB>([&](auto B_) {
+                constexpr int b = decltype(B_)::value;
+                const int k = (i0 + b * NT) & (P - 1);
+                static_for<1, R>([&](auto Q_) {
+                    constexpr int q = decltype(Q_)::value;
+                    float2 w = __ldg(tw + (q - 1) * P + k);
+                    if (INV) w.y = -w.y;
+                    r[b + q * NB] = cmul(r[b + q * NB], w);
+                });
+            });
+        }
+        // R-point DFTs
+        static_for<0, NB>([&](auto B_) {
+            constexpr int b = decltype(B_)::value;
+            float2 x[R];
+            static_for<0, R>([&](auto Q_) { constexpr int q = decltype(Q_)::value; x[q] = r[b + q * NB]; });
+            dft_regs<R, INV>(x);
+            static_for<0, R>([&](auto Q_) { constexpr int q = decltype(Q_)::value; r[b + q * NB] = x[q]; });
+        });
+        if constexpr (S + 1 < GEO::NSTAGES) {
+            if constexpr (S > 0) __syncthreads();      // everyone has finished reading the previous exchange
+            static_for<0, NB>([&](auto B_) {
+                constexpr int b = decltype(B_)::value;
+                const int i = i0 + b * NT;
+                const int k = i & (P - 1);
+                const int jbase = ((i >> LOGP) << (LOGP + LOGR)) | k;
+                static_for<0, R>([&](auto Q_) {
+                    constexpr int q = decltype(Q_)::value;
+                    smem[GEO::saddr(g, jbase + q * P)] = r[b + q * NB];
+                });
+            });
+            __syncthreads();
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------
+// exact unit roots
+// ---------------------------------------------------------------------------------------
+// 2^e as a float, e in [-126, 127]
+__device__ __forceinline__ float pow2f(int e) { return __int_as_float((127 + e) << 23); }
+
+// exp(sign * 2*pi*i * p / 2^logm), 0 <= p < 2^logm, sign = -1 forward / +1 inverse.
+// The angle is formed exactly (integer p, power-of-two scaling) before sincospif.
+__device__ __forceinline__ float2 unit_root(uint32_t p, int logm, bool inverse) {
+    float c, s;
+    if (logm <= 24) {
+        // fold to [-m/2, m/2): |p| <= 2^23 is exact in float and 2p/m is an exact scaling
+        const int32_t m = 1 << logm;
+        int32_t sp = (int32_t)p;
+        if (sp >= (m >> 1)) sp -= m;
+        sincospif((float)sp * pow2f(1 - logm), &s, &c);
+    } else {
+        const uint32_t lo = p & 4095u, hi = p >> 12;
+        float c1, s1, c2, s2;
+        sincospif((float)lo * pow2f(1 - logm), &s1, &c1);
+        const int32_t mh = 1 << (logm - 12);
+        int32_t sh = (int32_t)hi;
+        if (sh >= (mh >> 1)) sh -= mh;
+        sincospif((float)sh * pow2f(13 - logm), &s2, &c2);
+        c = c1 * c2 - s1 * s2;
+        s = c1 * s2 + s1 * c2;
+    }
+    return make_float2(c, inverse ? s : -s);
+}
+
+// tw[u] = root^(j*(i0 + u*step_rows)) for u = 0..E-1 with root = exp(sign*2*pi*i/2^logm):
+// the inter-pass twiddles of the rows a thread holds in column j.  step^(2^z) is evaluated
+// exactly for even z and by one squaring for odd z; tw[] is built as a product tree of depth
+// log2(E), so the worst-case error stays at a few ulp.
+template <int E>
+__device__ __forceinline__ void row_twiddles(float2 (&tw)[E], uint32_t j, uint32_t i0, uint32_t step_rows,
+                                             int logm, bool inverse) {
+    const uint32_t mask = (logm >= 32) ? 0xffffffffu : ((1u << logm) - 1u);
+    tw[0] = unit_root((j * i0) & mask, logm, inverse);
+    float2 pw = make_float2(1.f, 0.f);
+    static_for<0, ilog2(E)>([&](auto Z_) {
+        constexpr int z = decltype(Z_)::value;
+        if constexpr ((z & 1) == 0) pw = unit_root((j * (step_rows << z)) & mask, logm, inverse);
+        else pw = make_float2(pw.x * pw.x - pw.y * pw.y, 2.0f * pw.x * pw.y);
+        static_for<0, (1 << z)>([&](auto U_) {
+            constexpr int u = decltype(U_)::value;
+            tw[u + (1 << z)] = cmul(tw[u], pw);
+        });
+    });
+}
+
+}  // namespace rmx

@@ -1,0 +1,39 @@
+// Instantiations of the contiguous-pass kernels.
+#include "rmx_dispatch.h"
+
+namespace rmx {
+
+template <int LOGN, int LOGE, int MODE>
+static KernelEntry contig_entry() {
+    using GEO = TileGeom<LOGN, LOGE, false>;
+    return KernelEntry{(PassKernel)k_contig<LOGN, LOGE, MODE>, GEO::SMEM_BYTES, GEO::LOGG};
+}
+
+template <int LOGE, int MODE>
+static KernelEntry contig_by_logn(int logn) {
+    switch (logn - LOGE) {
+        case 0: return contig_entry<LOGE + 0, LOGE, MODE>();
+        case 1: return contig_entry<LOGE + 1, LOGE, MODE>();
+        case 2: return contig_entry<LOGE + 2, LOGE, MODE>();
+        case 3: return contig_entry<LOGE + 3, LOGE, MODE>();
+        case 4: return contig_entry<LOGE + 4, LOGE, MODE>();
+        case 5: return contig_entry<LOGE + 5, LOGE, MODE>();
+        case 6: return contig_entry<LOGE + 6, LOGE, MODE>();
+        case 7: return contig_entry<LOGE + 7, LOGE, MODE>();
+        case 8: return contig_entry<LOGE + 8, LOGE, MODE>();
+        default: return KernelEntry{nullptr, 0, 0};
+    }
+}
+
+KernelEntry get_contig_kernel(int logn, int loge, int mode) {
+    if (loge != 4) return KernelEntry{nullptr, 0, 0};
+    switch (mode) {
+        case C_FWD: return contig_by_logn<4, C_FWD>(logn);
+        case C_FWD_CU8: return contig_by_logn<4, C_FWD_CU8>(logn);
+        case C_INV_PAIR: return contig_by_logn<4, C_INV_PAIR>(logn);
+        case C_FWD_PSD: return contig_by_logn<4, C_FWD_PSD>(logn);
+        default: return KernelEntry{nullptr, 0, 0};
+    }
+}
+
+}  // namespace rmx

@@ -1,0 +1,269 @@
+// rmx_kernels.cuh — the tile kernels of the radio-mapper hot path (sm_100a).
+//
+// Data layout in HBM
+//   cu8 input   : uint8 [signal][2*N]   interleaved I,Q (rtl_sdr raw; reference buoy_node.py:392-398)
+//   spectrum    : float2[signal][L]     "digit-transposed": for pass lengths n_0..n_{m-1}
+//                 (n_0*...*n_{m-1} = L) position ((k_0*n_1 + k_1)*n_2 + ...) + k_{m-1} holds
+//                 frequency bin k_0 + n_0*(k_1 + n_1*(k_2 + ...)).  Both FFT directions run
+//                 in place on this layout with no transposes; element-wise products are
+//                 layout-agnostic.  Single-pass plans (L <= TILE) are natural order.
+//   correlation : float2[pair][L]       workspace between the inverse passes
+//
+// Forward  (DIF):  pass t = column FFTs of length n_t at stride s_t = n_{t+1}*...*n_{m-1},
+//                  then multiply by w_{M_t}^{j*k} (M_t = n_t*s_t, j = column, k = output row);
+//                  the last pass (s = 1) is the contiguous kernel.
+// Inverse  (DIT):  the same passes in reverse order with conjugate twiddles applied on the
+//                  INPUT of each column pass; the last pass to run (pass 0) yields natural-order
+//                  lags and is fused with the |c|^2 arg-max.
+#pragma once
+#include "rmx_fft_core.cuh"
+
+namespace rmx {
+
+struct Partial {
+    float val;     // |c|^2 of the best lag in this tile (-1 = none)
+    int32_t lag;   // signed lag
+};
+
+struct PassParams {
+    const float2* src;        // float2 input of in-place passes / correlation workspace
+    float2* dst;              // float2 output
+    const uint8_t* cu8;       // raw IQ input (FWD_CU8 modes)
+    const float* window;      // optional per-sample window (Welch), nullptr = none
+    const float2* spectra;    // spectra base for the pair product
+    const int2* pairs;        // (i, j) signal indices per pair
+    Partial* partials;        // arg-max partials [item][tiles_per_item]
+    float* accum;             // PSD accumulator (PSD mode)
+    StageTables tabs;
+    long long n_samples;      // valid samples per signal (N); the rest of L is zero padding
+    long long cu8_stride;     // bytes between consecutive signals in cu8
+    long long src_item_stride;  // elements between consecutive items of src/dst (normally L)
+    int n_items;              // signals or pairs covered by this launch
+    int logL;                 // log2 of the full transform length
+    int logS;                 // log2 of the column stride (column kernels)
+    int lag_pos_max;          // arg-max searches lags in [-lag_neg_max, lag_pos_max]
+    int lag_neg_max;
+    int items_per_cta;        // PSD mode: signals accumulated by one CTA
+    float scale;              // scale folded into the pair product (1/L)
+};
+
+enum ContigMode { C_FWD = 0, C_FWD_CU8 = 1, C_INV_PAIR = 2, C_FWD_PSD = 3 };
+enum ColMode { K_FWD_CU8 = 0, K_FWD = 1, K_INV = 2, K_INV_ARGMAX = 3 };
+
+__device__ __forceinline__ float2 load_cu8_sample(const uint8_t* base, long long idx) {
+    // (float)u8 - 127.5f, I then Q: exactly the reference's unpack (buoy_node.py:392-398)
+    const uchar2 b = *reinterpret_cast<const uchar2*>(base + 2 * idx);
+    return make_float2((float)b.x - 127.5f, (float)b.y - 127.5f);
+}
+
+__device__ __forceinline__ bool better(float v, int lag, float bv, int blag) {
+    // np.argmax semantics on the lag-ordered 'full' output: first (lowest-lag) maximum wins
+    return v > bv || (v == bv && lag < blag);
+}
+
+// Block-wide arg-max of (val, lag); result valid in thread 0.
+__device__ __forceinline__ void block_argmax(float& v, int& lag) {
+    __shared__ float s_v[kThreads / 32];
+    __shared__ int s_l[kThreads / 32];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, off);
+        const int ol = __shfl_xor_sync(0xffffffffu, lag, off);
+        if (better(ov, ol, v, lag)) { v = ov; lag = ol; }
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_v[w] = v; s_l[w] = lag; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = threadIdx.x < kThreads / 32 ? s_v[threadIdx.x] : -1.f;
+        lag = threadIdx.x < kThreads / 32 ? s_l[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, off);
+            const int ol = __shfl_xor_sync(0xffffffffu, lag, off);
+            if (better(ov, ol, v, lag)) { v = ov; lag = ol; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// contiguous pass: FFTs over rows of n consecutive elements
+// ---------------------------------------------------------------------------------------
+template <int LOGN, int LOGE, int MODE>
+__global__ void __launch_bounds__(kThreads) k_contig(const PassParams p) {
+    using GEO = TileGeom<LOGN, LOGE, false>;
+    constexpr int E = GEO::E, NT = GEO::NT, G = GEO::G;
+    constexpr bool INV = (MODE == C_INV_PAIR);
+    extern __shared__ float2 smem[];
+
+    int g, i0;
+    GEO::thread_map(threadIdx.x, g, i0);
+    const int log_rows = p.logL - LOGN;               // rows per item (log2)
+    float2 r[E];
+
+    if constexpr (MODE == C_FWD_PSD) {
+        // Welch: accumulate |X|^2 of the same rows over items_per_cta consecutive signals.
+        // grid = (tiles_per_signal, signal chunks)
+        float acc[E];
+#pragma unroll
+        for (int u = 0; u < E; ++u) acc[u] = 0.f;
+        const long long row = (long long)blockIdx.x * G + g;          // row within a signal
+        const int first = blockIdx.y * p.items_per_cta;
+        const int last = min(first + p.items_per_cta, p.n_items);
+        for (int it = first; it < last; ++it) {
+            const float2* __restrict__ in = p.src + (long long)it * p.src_item_stride + (row << LOGN);
+#pragma unroll
+            for (int u = 0; u < E; ++u) r[u] = in[i0 + u * NT];
+            fft_tile<GEO, false>(r, smem, g, i0, p.tabs);
+#pragma unroll
+            for (int u = 0; u < E; ++u) acc[u] += cnorm2(r[u]);
+            if constexpr (GEO::NSTAGES > 1) __syncthreads();          // exchange buffer is reused
+        }
+        float* __restrict__ out = p.accum + (row << LOGN);
+#pragma unroll
+        for (int u = 0; u < E; ++u) atomicAdd(out + i0 + u * NT, acc[u]);
+        return;
+    } else {
+        // decode (item, row)
+        long long item, row;
+        if (log_rows >= GEO::LOGG) {
+            // item-fastest tile order: CTAs that run together touch the same rows of
+            // different pairs, so each spectrum row is fetched from HBM once and then hit in L2
+            item = blockIdx.x % (unsigned)p.n_items;
+            row = (long long)(blockIdx.x / (unsigned)p.n_items) * G + g;
+        } else {
+            const long long flat = (long long)blockIdx.x * G + g;
+            item = flat >> log_rows;
+            row = flat & ((1LL << log_rows) - 1);
+        }
+        const bool active = item < p.n_items;
+
+        if constexpr (MODE == C_FWD) {
+            const float2* __restrict__ in = p.src + item * p.src_item_stride + (row << LOGN);
+#pragma unroll
+            for (int u = 0; u < E; ++u) r[u] = active ? in[i0 + u * NT] : make_float2(0.f, 0.f);
+        } else if constexpr (MODE == C_FWD_CU8) {
+            // single-pass plans only (n == L, one row per signal)
+            const uint8_t* __restrict__ in = p.cu8 + item * p.cu8_stride;
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+                const long long idx = (row << LOGN) + i0 + u * NT;
+                r[u] = (active && idx < p.n_samples) ? load_cu8_sample(in, idx) : make_float2(0.f, 0.f);
+            }
+        } else {  // C_INV_PAIR
+            int2 pr = make_int2(0, 0);
+            if (active) pr = p.pairs[item];
+            const float2* __restrict__ xi = p.spectra + ((long long)pr.x << p.logL) + (row << LOGN);
+            const float2* __restrict__ xj = p.spectra + ((long long)pr.y << p.logL) + (row << LOGN);
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+                if (active) {
+                    const float2 a = __ldg(xi + i0 + u * NT), b = __ldg(xj + i0 + u * NT);
+                    const float2 c = cmul_conj(b, a);              // X_j * conj(X_i)
+                    r[u] = make_float2(c.x * p.scale, c.y * p.scale);
+                } else {
+                    r[u] = make_float2(0.f, 0.f);
+                }
+            }
+        }
+
+        fft_tile<GEO, INV>(r, smem, g, i0, p.tabs);
+
+        if (active) {
+            float2* __restrict__ out = p.dst + item * p.src_item_stride + (row << LOGN);
+#pragma unroll
+            for (int u = 0; u < E; ++u) out[i0 + u * NT] = r[u];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// column pass: FFTs of length n at element stride s = 2^logS, G adjacent columns per tile
+// ---------------------------------------------------------------------------------------
+template <int LOGN, int LOGE, int MODE>
+__global__ void __launch_bounds__(kThreads) k_col(const PassParams p) {
+    using GEO = TileGeom<LOGN, LOGE, true>;
+    constexpr int E = GEO::E, NT = GEO::NT, G = GEO::G, LOGG = GEO::LOGG;
+    constexpr bool INV = (MODE == K_INV || MODE == K_INV_ARGMAX);
+    extern __shared__ float2 smem[];
+
+    int g, i0;
+    GEO::thread_map(threadIdx.x, g, i0);
+    const int logS = p.logS;
+    const int logM = LOGN + logS;
+    const int log_tpb = logS - LOGG;                       // tiles per block (log2)
+    const int log_bpi = p.logL - logM;                     // blocks per item (log2)
+    const unsigned idx = blockIdx.x;
+    const unsigned jt = idx & ((1u << log_tpb) - 1u);
+    const unsigned rest = idx >> log_tpb;
+    const unsigned beta = rest & ((1u << log_bpi) - 1u);
+    const long long item = rest >> log_bpi;
+    const unsigned j = (jt << LOGG) + g;                   // column within the block
+    const long long base = ((long long)beta << logM) + j;  // element offset inside the item
+
+    float2 r[E];
+    if constexpr (MODE == K_FWD_CU8) {
+        const uint8_t* __restrict__ in = p.cu8 + item * p.cu8_stride;
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+            const long long sidx = base + ((long long)(i0 + u * NT) << logS);
+            float2 v = make_float2(0.f, 0.f);
+            if (sidx < p.n_samples) {
+                v = load_cu8_sample(in, sidx);
+                if (p.window != nullptr) { const float w = __ldg(p.window + sidx); v.x *= w; v.y *= w; }
+            }
+            r[u] = v;
+        }
+    } else {
+        const float2* __restrict__ in = p.src + item * p.src_item_stride + base;
+#pragma unroll
+        for (int u = 0; u < E; ++u) r[u] = in[(long long)(i0 + u * NT) << logS];
+    }
+
+    if constexpr (INV) {
+        float2 tw[E];
+        row_twiddles<E>(tw, j, (uint32_t)i0, (uint32_t)NT, logM, true);
+#pragma unroll
+        for (int u = 0; u < E; ++u) r[u] = cmul(r[u], tw[u]);
+    }
+
+    fft_tile<GEO, INV>(r, smem, g, i0, p.tabs);
+
+    if constexpr (!INV) {
+        float2 tw[E];
+        row_twiddles<E>(tw, j, (uint32_t)i0, (uint32_t)NT, logM, false);
+#pragma unroll
+        for (int u = 0; u < E; ++u) r[u] = cmul(r[u], tw[u]);
+    }
+
+    if constexpr (MODE == K_INV_ARGMAX) {
+        // pass 0 of the inverse: row m1, column j  ->  lag index m = m1*s + j (natural order)
+        const long long Lfull = 1LL << p.logL;
+        float bv = -1.f;
+        int blag = 0x7fffffff;
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+            const long long m = base + ((long long)(i0 + u * NT) << logS);
+            int lag;
+            bool ok;
+            if (m <= p.lag_pos_max) { lag = (int)m; ok = true; }
+            else { lag = (int)(m - Lfull); ok = (m - Lfull) >= -(long long)p.lag_neg_max; }
+            const float v = cnorm2(r[u]);
+            if (ok && better(v, lag, bv, blag)) { bv = v; blag = lag; }
+        }
+        if constexpr (GEO::NSTAGES > 1) __syncthreads();
+        block_argmax(bv, blag);
+        if (threadIdx.x == 0) {
+            Partial out;
+            out.val = bv;
+            out.lag = blag;
+            p.partials[(item << log_tpb) + jt] = out;
+        }
+    } else {
+        float2* __restrict__ out = p.dst + item * p.src_item_stride + base;
+#pragma unroll
+        for (int u = 0; u < E; ++u) out[(long long)(i0 + u * NT) << logS] = r[u];
+    }
+}
+
+}  // namespace rmx

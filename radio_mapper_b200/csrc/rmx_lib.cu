@@ -1,0 +1,819 @@
+// rmx_lib.cu — plan management, pass scheduling, small kernels and the C ABI (include/rmx.h).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "../../include/rmx.h"
+#include "rmx_dispatch.h"
+
+using namespace rmx;
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(RMX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCH_CHECK(name)                                                                  \
+    do {                                                                                    \
+        cudaError_t e_ = cudaGetLastError();                                                \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(RMX_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char* rmx_last_error(void) { return g_err; }
+extern "C" int rmx_version(void) { return RMX_VERSION; }
+
+// ---------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------
+struct rmx_plan {
+    int n_signals = 0;
+    long long n_samples = 0;
+    int logL = 0;
+    int loge = 4;
+    int n_passes = 0;
+    int logn[kMaxStages + 2] = {0};   // pass t transform length
+    int logs[kMaxStages + 2] = {0};   // pass t column stride (0 for the contiguous pass)
+    StageTables tabs[kMaxStages + 2];
+    std::vector<void*> dev_allocs;
+    float* d_hann = nullptr;
+    double hann_sumsq = 0.0;
+    long long lag_pos_max = 0, lag_neg_max = 0;
+};
+
+static int build_stage_tables(rmx_plan* pl, int logn, int loge, StageTables* out) {
+    memset(out, 0, sizeof(*out));
+    const int nstages = (logn + loge - 1) / loge;
+    for (int s = 1; s < nstages; ++s) {
+        const int logp = s * loge;
+        const int logr = std::min(loge, logn - logp);
+        const int P = 1 << logp, R = 1 << logr;
+        std::vector<float2> h((size_t)(R - 1) * P);
+        const double m = (double)P * R;
+        for (int q = 1; q < R; ++q)
+            for (int k = 0; k < P; ++k) {
+                // exact angle reduction in integers
+                const long long e = ((long long)q * k) % (long long)(P * R);
+                const double a = -2.0 * M_PI * (double)e / m;
+                h[(size_t)(q - 1) * P + k] = make_float2((float)cos(a), (float)sin(a));
+            }
+        float2* d = nullptr;
+        CUDA_TRY(cudaMalloc(&d, h.size() * sizeof(float2)));
+        pl->dev_allocs.push_back(d);
+        CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        out->tw[s] = d;
+    }
+    return RMX_OK;
+}
+
+static int choose_passes(rmx_plan* pl) {
+    const int loge = pl->loge, logL = pl->logL;
+    const int maxc = max_contig_logn(loge), maxk = max_col_logn(loge), minn = min_logn(loge);
+    if (logL < minn) return fail(RMX_ERR_UNSUPPORTED, "fft_len 2^%d is below the minimum 2^%d", logL, minn);
+    if (logL <= maxc) {
+        pl->n_passes = 1;
+        pl->logn[0] = logL;
+        pl->logs[0] = 0;
+        return RMX_OK;
+    }
+    const int contig = std::min(maxc, logL - minn);
+    int rem = logL - contig;
+    const int ncol = (rem + maxk - 1) / maxk;
+    if (ncol + 1 > kMaxStages + 1) return fail(RMX_ERR_UNSUPPORTED, "fft_len 2^%d needs too many passes", logL);
+    int stride = logL;
+    for (int t = 0; t < ncol; ++t) {
+        // smaller transforms first: the outermost pass then has the most columns per tile
+        const int a = rem / (ncol - t);
+        pl->logn[t] = a;
+        stride -= a;
+        pl->logs[t] = stride;
+        rem -= a;
+        if (a < minn || a > maxk) return fail(RMX_ERR_UNSUPPORTED, "no pass split for fft_len 2^%d", logL);
+    }
+    pl->logn[ncol] = contig;
+    pl->logs[ncol] = 0;
+    pl->n_passes = ncol + 1;
+    return RMX_OK;
+}
+
+extern "C" int rmx_plan_create(rmx_plan** out, int n_signals, size_t n_samples, size_t fft_len, unsigned flags) {
+    if (!out) return fail(RMX_ERR_ARG, "plan pointer is null");
+    *out = nullptr;
+    if (n_signals <= 0) return fail(RMX_ERR_ARG, "n_signals must be positive (got %d)", n_signals);
+    if (n_samples == 0 || n_samples > fft_len) return fail(RMX_ERR_ARG, "need 0 < n_samples <= fft_len");
+    if (fft_len & (fft_len - 1)) return fail(RMX_ERR_UNSUPPORTED, "fft_len must be a power of two (got %zu)", fft_len);
+    if (fft_len > (size_t(1) << 30)) return fail(RMX_ERR_UNSUPPORTED, "fft_len above 2^30 is not supported");
+    (void)flags;
+    rmx_plan* pl = new rmx_plan();
+    pl->n_signals = n_signals;
+    pl->n_samples = (long long)n_samples;
+    pl->logL = 0;
+    while ((size_t(1) << pl->logL) < fft_len) ++pl->logL;
+    int rc = choose_passes(pl);
+    for (int t = 0; rc == RMX_OK && t < pl->n_passes; ++t) rc = build_stage_tables(pl, pl->logn[t], pl->loge, &pl->tabs[t]);
+    if (rc != RMX_OK) {
+        rmx_plan_destroy(pl);
+        return rc;
+    }
+    rmx_plan_set_max_lag(pl, -1);
+    *out = pl;
+    return RMX_OK;
+}
+
+extern "C" int rmx_plan_destroy(rmx_plan* pl) {
+    if (!pl) return RMX_OK;
+    for (void* p : pl->dev_allocs) cudaFree(p);
+    delete pl;
+    return RMX_OK;
+}
+
+extern "C" int rmx_plan_layout(const rmx_plan* pl, int32_t* pass_lengths, int cap) {
+    if (!pl) return fail(RMX_ERR_ARG, "plan is null");
+    for (int t = 0; t < pl->n_passes && t < cap; ++t) pass_lengths[t] = 1 << pl->logn[t];
+    return pl->n_passes;
+}
+
+extern "C" int rmx_plan_set_max_lag(rmx_plan* pl, long long max_lag) {
+    if (!pl) return fail(RMX_ERR_ARG, "plan is null");
+    const long long L = 1LL << pl->logL;
+    // lags representable without aliasing: |lag| <= min(N-1, L-N)
+    long long full = std::min(pl->n_samples - 1, L - pl->n_samples);
+    if (pl->n_samples * 2 - 1 <= L) full = pl->n_samples - 1;
+    long long m = (max_lag < 0) ? full : std::min(max_lag, full);
+    pl->lag_pos_max = m;
+    pl->lag_neg_max = m;
+    return RMX_OK;
+}
+
+static int tiles_per_item_pass0(const rmx_plan* pl) {
+    // arg-max partials produced per pair by the outermost inverse pass
+    if (pl->n_passes == 1) return 1;
+    const int logG = kLogThreads + pl->loge - pl->logn[0];
+    return 1 << (pl->logs[0] - logG);
+}
+
+extern "C" size_t rmx_plan_workspace_bytes(const rmx_plan* pl, int n_pairs) {
+    if (!pl || n_pairs <= 0) return 0;
+    const size_t L = size_t(1) << pl->logL;
+    return (size_t)n_pairs * (L * sizeof(float2) + (size_t)tiles_per_item_pass0(pl) * sizeof(Partial)) + 256;
+}
+
+// ---------------------------------------------------------------------------------------
+// pass launchers
+// ---------------------------------------------------------------------------------------
+static int launch_pass(const KernelEntry& k, const char* name, dim3 grid, const PassParams& pp, cudaStream_t st) {
+    if (!k.fn) return fail(RMX_ERR_UNSUPPORTED, "kernel %s is not instantiated for this size", name);
+    if (k.smem_bytes > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute((const void*)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem_bytes));
+    k.fn<<<grid, kThreads, k.smem_bytes, st>>>(pp);
+    LAUNCH_CHECK(name);
+    return RMX_OK;
+}
+
+static PassParams base_params(const rmx_plan* pl) {
+    PassParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.logL = pl->logL;
+    pp.n_samples = pl->n_samples;
+    pp.cu8_stride = 2 * pl->n_samples;
+    pp.src_item_stride = 1LL << pl->logL;
+    pp.lag_pos_max = (int)pl->lag_pos_max;
+    pp.lag_neg_max = (int)pl->lag_neg_max;
+    pp.scale = 1.0f;
+    return pp;
+}
+
+static unsigned tiles_of(const rmx_plan* pl, long long n_items) {
+    const int logtile = kLogThreads + pl->loge;
+    const long long total = n_items << pl->logL;
+    return (unsigned)((total + (1LL << logtile) - 1) >> logtile);
+}
+
+// forward FFT of n_items signals from cu8 (optionally windowed) into `spectra`
+static int forward_cu8(const rmx_plan* pl, const uint8_t* iq, float2* spectra, int n_items, const float* window,
+                       cudaStream_t st) {
+    const int np = pl->n_passes;
+    PassParams pp = base_params(pl);
+    pp.n_items = n_items;
+    pp.cu8 = iq;
+    pp.window = window;
+    pp.dst = spectra;
+    pp.src = spectra;
+    const unsigned grid = tiles_of(pl, n_items);
+    if (np == 1) {
+        if (window) return fail(RMX_ERR_UNSUPPORTED, "windowed single-pass forward is handled by the caller");
+        pp.tabs = pl->tabs[0];
+        return launch_pass(get_contig_kernel(pl->logn[0], pl->loge, C_FWD_CU8), "contig_fwd_cu8", dim3(grid), pp, st);
+    }
+    for (int t = 0; t < np - 1; ++t) {
+        pp.tabs = pl->tabs[t];
+        pp.logS = pl->logs[t];
+        int rc = launch_pass(get_col_kernel(pl->logn[t], pl->loge, t == 0 ? K_FWD_CU8 : K_FWD),
+                             t == 0 ? "col_fwd_cu8" : "col_fwd", dim3(grid), pp, st);
+        if (rc) return rc;
+    }
+    pp.tabs = pl->tabs[np - 1];
+    return launch_pass(get_contig_kernel(pl->logn[np - 1], pl->loge, C_FWD), "contig_fwd", dim3(grid), pp, st);
+}
+
+extern "C" int rmx_fft_forward_cu8(const rmx_plan* pl, const uint8_t* iq, rmx_complex64* spectra, void* stream) {
+    if (!pl || !iq || !spectra) return fail(RMX_ERR_ARG, "null argument to rmx_fft_forward_cu8");
+    return forward_cu8(pl, iq, reinterpret_cast<float2*>(spectra), pl->n_signals, nullptr, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------
+// lag-search finalisation
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 block_sum3(float2 v, float2* sh) {
+    // sum of v over the block (128 threads); result broadcast
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, off);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float2 t = make_float2(0.f, 0.f);
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t.x += sh[w].x; t.y += sh[w].y; }
+    return t;
+}
+
+__device__ __forceinline__ float parabolic(float ym, float y0, float yp) {
+    const double den = (double)ym - 2.0 * (double)y0 + (double)yp;
+    if (den == 0.0) return 0.f;
+    return (float)(0.5 * ((double)ym - (double)yp) / den);
+}
+
+// multi-pass plans: reduce the tile partials, then evaluate c[m-1], c[m], c[m+1] by direct
+// n_0-term sums over the input of the outermost inverse pass (still in the workspace).
+__global__ void __launch_bounds__(128) k_finalize_sum(const Partial* __restrict__ partials, int tiles_per_item,
+                                                      const float2* __restrict__ D, int logL, int logn0, int logs0,
+                                                      int lag_pos_max, int lag_neg_max, rmx_peak* __restrict__ out) {
+    __shared__ float s_v[4];
+    __shared__ int s_l[4];
+    __shared__ float2 s_sum[4];
+    const int item = blockIdx.x;
+    float bv = -1.f;
+    int blag = 0x7fffffff;
+    for (int t = threadIdx.x; t < tiles_per_item; t += blockDim.x) {
+        const Partial p = partials[(long long)item * tiles_per_item + t];
+        if (p.val >= 0.f && better(p.val, p.lag, bv, blag)) { bv = p.val; blag = p.lag; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int ol = __shfl_xor_sync(0xffffffffu, blag, off);
+        if (better(ov, ol, bv, blag)) { bv = ov; blag = ol; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_l[threadIdx.x >> 5] = blag; }
+    __syncthreads();
+    bv = s_v[0]; blag = s_l[0];
+    for (int w = 1; w < 4; ++w) if (better(s_v[w], s_l[w], bv, blag)) { bv = s_v[w]; blag = s_l[w]; }
+
+    const long long L = 1LL << logL;
+    const int n0 = 1 << logn0;
+    const float2* __restrict__ Dp = D + ((long long)item << logL);
+    float y[3];
+    for (int d = -1; d <= 1; ++d) {
+        const long long lag = (long long)blag + d;
+        float2 acc = make_float2(0.f, 0.f);
+        const bool in_range = (lag >= -(long long)lag_neg_max) && (lag <= (long long)lag_pos_max);
+        if (in_range) {
+            const unsigned long long m = (unsigned long long)(lag < 0 ? lag + L : lag);
+            const unsigned long long j = m & ((1ULL << logs0) - 1ULL);
+            for (int k = threadIdx.x; k < n0; k += blockDim.x) {
+                const float2 v = Dp[((long long)k << logs0) + (long long)j];
+                const unsigned long long e = ((unsigned long long)k * m) & (unsigned long long)(L - 1);
+                const float2 w = unit_root((uint32_t)e, logL, true);
+                const float2 t = cmul(v, w);
+                acc.x += t.x; acc.y += t.y;
+            }
+        }
+        const float2 tot = block_sum3(acc, s_sum);
+        y[d + 1] = in_range ? sqrtf(tot.x * tot.x + tot.y * tot.y) : -1.f;
+    }
+    if (threadIdx.x == 0) {
+        rmx_peak r;
+        r.lag = blag;
+        r.peak = y[1];
+        r.frac = (y[0] >= 0.f && y[2] >= 0.f) ? parabolic(y[0], y[1], y[2]) : 0.f;
+        r.pad = bv;
+        out[item] = r;
+    }
+}
+
+// single-pass plans: the workspace already holds c in natural order
+__global__ void __launch_bounds__(128) k_finalize_direct(const float2* __restrict__ C, int logL, int lag_pos_max,
+                                                         int lag_neg_max, rmx_peak* __restrict__ out) {
+    __shared__ float s_v[4];
+    __shared__ int s_l[4];
+    const int item = blockIdx.x;
+    const long long L = 1LL << logL;
+    const float2* __restrict__ c = C + ((long long)item << logL);
+    float bv = -1.f;
+    int blag = 0x7fffffff;
+    for (long long m = threadIdx.x; m < L; m += blockDim.x) {
+        int lag;
+        bool ok;
+        if (m <= lag_pos_max) { lag = (int)m; ok = true; }
+        else { lag = (int)(m - L); ok = (m - L) >= -(long long)lag_neg_max; }
+        const float v = cnorm2(c[m]);
+        if (ok && better(v, lag, bv, blag)) { bv = v; blag = lag; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int ol = __shfl_xor_sync(0xffffffffu, blag, off);
+        if (better(ov, ol, bv, blag)) { bv = ov; blag = ol; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_l[threadIdx.x >> 5] = blag; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bv = s_v[0]; blag = s_l[0];
+        for (int w = 1; w < 4; ++w) if (better(s_v[w], s_l[w], bv, blag)) { bv = s_v[w]; blag = s_l[w]; }
+        float y[3];
+        for (int d = -1; d <= 1; ++d) {
+            const long long lag = (long long)blag + d;
+            if (lag < -(long long)lag_neg_max || lag > (long long)lag_pos_max) { y[d + 1] = -1.f; continue; }
+            const float2 v = c[lag < 0 ? lag + L : lag];
+            y[d + 1] = sqrtf(v.x * v.x + v.y * v.y);
+        }
+        rmx_peak r;
+        r.lag = blag;
+        r.peak = y[1];
+        r.frac = (y[0] >= 0.f && y[2] >= 0.f) ? parabolic(y[0], y[1], y[2]) : 0.f;
+        r.pad = bv;
+        out[item] = r;
+    }
+}
+
+extern "C" int rmx_xcorr_pairs_peak(const rmx_plan* pl, const rmx_complex64* spectra, const rmx_pair* pairs,
+                                    int n_pairs, rmx_peak* out, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+    if (!pl || !spectra || !pairs || !out || !workspace) return fail(RMX_ERR_ARG, "null argument to rmx_xcorr_pairs_peak");
+    if (n_pairs <= 0) return RMX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t L = size_t(1) << pl->logL;
+    const int tpi = tiles_per_item_pass0(pl);
+    const size_t per_pair = L * sizeof(float2) + (size_t)tpi * sizeof(Partial);
+    if (workspace_bytes < per_pair + 256)
+        return fail(RMX_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one pair (%zu needed)", workspace_bytes,
+                    per_pair + 256);
+    const int chunk = (int)std::min<size_t>((size_t)n_pairs, (workspace_bytes - 256) / per_pair);
+    float2* D = reinterpret_cast<float2*>(workspace);
+    Partial* partials = reinterpret_cast<Partial*>(reinterpret_cast<char*>(workspace) + (((size_t)chunk * L * sizeof(float2) + 255) & ~size_t(255)));
+    const int np = pl->n_passes;
+
+    for (int first = 0; first < n_pairs; first += chunk) {
+        const int cnt = std::min(chunk, n_pairs - first);
+        PassParams pp = base_params(pl);
+        pp.n_items = cnt;
+        pp.spectra = reinterpret_cast<const float2*>(spectra);
+        pp.pairs = reinterpret_cast<const int2*>(pairs) + first;
+        pp.src = D;
+        pp.dst = D;
+        pp.partials = partials;
+        pp.scale = 1.0f / (float)L;
+        const unsigned grid = tiles_of(pl, cnt);
+        // innermost pass first: rows of X_j * conj(X_i)
+        pp.tabs = pl->tabs[np - 1];
+        int rc = launch_pass(get_contig_kernel(pl->logn[np - 1], pl->loge, C_INV_PAIR), "contig_inv_pair", dim3(grid), pp, st);
+        if (rc) return rc;
+        for (int t = np - 2; t >= 0; --t) {
+            pp.tabs = pl->tabs[t];
+            pp.logS = pl->logs[t];
+            rc = launch_pass(get_col_kernel(pl->logn[t], pl->loge, t == 0 ? K_INV_ARGMAX : K_INV),
+                             t == 0 ? "col_inv_argmax" : "col_inv", dim3(grid), pp, st);
+            if (rc) return rc;
+        }
+        if (np == 1) {
+            k_finalize_direct<<<cnt, 128, 0, st>>>(D, pl->logL, (int)pl->lag_pos_max, (int)pl->lag_neg_max, out + first);
+            LAUNCH_CHECK("finalize_direct");
+        } else {
+            k_finalize_sum<<<cnt, 128, 0, st>>>(partials, tpi, D, pl->logL, pl->logn[0], pl->logs[0],
+                                                (int)pl->lag_pos_max, (int)pl->lag_neg_max, out + first);
+            LAUNCH_CHECK("finalize_sum");
+        }
+    }
+    return RMX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// layout helpers, dB spectrum
+// ---------------------------------------------------------------------------------------
+struct LayoutDesc {
+    int n_passes;
+    int logn[kMaxStages + 2];
+    int logs[kMaxStages + 2];
+};
+
+static LayoutDesc layout_of(const rmx_plan* pl) {
+    LayoutDesc d;
+    d.n_passes = pl->n_passes;
+    for (int t = 0; t < kMaxStages + 2; ++t) { d.logn[t] = pl->logn[t]; d.logs[t] = pl->logs[t]; }
+    return d;
+}
+
+// frequency bin stored at position pos of the digit-transposed layout
+__device__ __forceinline__ long long layout_freq(const LayoutDesc& d, long long pos) {
+    long long f = 0;
+    int weight = 0;
+    for (int t = 0; t < d.n_passes; ++t) {
+        const long long digit = (pos >> d.logs[t]) & ((1LL << d.logn[t]) - 1);
+        f |= digit << weight;
+        weight += d.logn[t];
+    }
+    return f;
+}
+
+__global__ void k_spectrum_natural(LayoutDesc d, const float2* __restrict__ in, float2* __restrict__ out, int logL,
+                                   long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pos = i & ((1LL << logL) - 1);
+        out[(i - pos) + layout_freq(d, pos)] = in[i];
+    }
+}
+
+__global__ void k_spectrum_db(LayoutDesc d, const float2* __restrict__ in, float* __restrict__ out, int logL,
+                              long long total, int shift) {
+    const long long L = 1LL << logL;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pos = i & (L - 1);
+        long long f = layout_freq(d, pos);
+        if (shift) f = (f + (L >> 1)) & (L - 1);
+        const float2 v = in[i];
+        // 20*log10(|X| + 1e-12): buoy_node.py:405
+        out[(i - pos) + f] = 20.0f * log10f(hypotf(v.x, v.y) + 1e-12f);
+    }
+}
+
+static unsigned grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    return (unsigned)std::min<long long>(g, 148LL * 16);
+}
+
+extern "C" int rmx_spectrum_natural(const rmx_plan* pl, const rmx_complex64* spectra, rmx_complex64* out,
+                                    int n_signals, void* stream) {
+    if (!pl || !spectra || !out) return fail(RMX_ERR_ARG, "null argument to rmx_spectrum_natural");
+    if ((const void*)spectra == (const void*)out) return fail(RMX_ERR_ARG, "rmx_spectrum_natural cannot run in place");
+    const long long total = (long long)n_signals << pl->logL;
+    k_spectrum_natural<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        layout_of(pl), reinterpret_cast<const float2*>(spectra), reinterpret_cast<float2*>(out), pl->logL, total);
+    LAUNCH_CHECK("spectrum_natural");
+    return RMX_OK;
+}
+
+extern "C" int rmx_spectrum_db(const rmx_plan* pl, const rmx_complex64* spectra, float* out_db, int n_signals,
+                               int shift, void* stream) {
+    if (!pl || !spectra || !out_db) return fail(RMX_ERR_ARG, "null argument to rmx_spectrum_db");
+    const long long total = (long long)n_signals << pl->logL;
+    k_spectrum_db<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        layout_of(pl), reinterpret_cast<const float2*>(spectra), out_db, pl->logL, total, shift);
+    LAUNCH_CHECK("spectrum_db");
+    return RMX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// stage 1 stand-alone: cu8 -> complex64
+// ---------------------------------------------------------------------------------------
+// Each thread converts 16 input bytes (one 128-bit load, 8 samples) and writes four float4.
+__global__ void __launch_bounds__(256) k_unpack_cu8(const uint8_t* __restrict__ in, float2* __restrict__ out, size_t n) {
+    const size_t nvec = n / 8;
+    const uint4* __restrict__ in4 = reinterpret_cast<const uint4*>(in);
+    float4* __restrict__ out4 = reinterpret_cast<float4*>(out);
+    for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+        const uint4 w = __ldg(in4 + v);
+        const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float4 o;
+            o.x = (float)(ws[k] & 0xffu) - 127.5f;
+            o.y = (float)((ws[k] >> 8) & 0xffu) - 127.5f;
+            o.z = (float)((ws[k] >> 16) & 0xffu) - 127.5f;
+            o.w = (float)(ws[k] >> 24) - 127.5f;
+            out4[v * 4 + k] = o;
+        }
+    }
+    // tail (n not a multiple of 8)
+    for (size_t i = nvec * 8 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = make_float2((float)in[2 * i] - 127.5f, (float)in[2 * i + 1] - 127.5f);
+}
+
+__global__ void __launch_bounds__(256) k_unpack_cu8_scalar(const uint8_t* __restrict__ in, float2* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = make_float2((float)in[2 * i] - 127.5f, (float)in[2 * i + 1] - 127.5f);
+}
+
+extern "C" int rmx_unpack_cu8(const uint8_t* in, rmx_complex64* out, size_t n_samples, void* stream) {
+    if (n_samples == 0) return RMX_OK;
+    if (!in || !out) return fail(RMX_ERR_ARG, "null argument to rmx_unpack_cu8");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool aligned = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    if (aligned) {
+        k_unpack_cu8<<<grid_for((long long)(n_samples + 7) / 8, 256), 256, 0, st>>>(in, reinterpret_cast<float2*>(out), n_samples);
+    } else {
+        k_unpack_cu8_scalar<<<grid_for((long long)n_samples, 256), 256, 0, st>>>(in, reinterpret_cast<float2*>(out), n_samples);
+    }
+    LAUNCH_CHECK("unpack_cu8");
+    return RMX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Welch PSD
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_unpack_window(const uint8_t* __restrict__ in, const float* __restrict__ w,
+                                                       float2* __restrict__ out, int logL, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const float ww = w[i & ((1LL << logL) - 1)];
+        out[i] = make_float2(((float)in[2 * i] - 127.5f) * ww, ((float)in[2 * i + 1] - 127.5f) * ww);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_psd_finalize(LayoutDesc d, const float* __restrict__ accum, float* __restrict__ psd,
+                                                      int logL, float scale) {
+    const long long L = 1LL << logL;
+    for (long long pos = blockIdx.x * (long long)blockDim.x + threadIdx.x; pos < L; pos += (long long)gridDim.x * blockDim.x)
+        psd[layout_freq(d, pos)] = accum[pos] * scale;
+}
+
+static int ensure_hann(rmx_plan* pl) {
+    if (pl->d_hann) return RMX_OK;
+    const size_t L = size_t(1) << pl->logL;
+    std::vector<float> h(L);
+    double ss = 0.0;
+    for (size_t n = 0; n < L; ++n) {
+        // periodic Hann == scipy.signal.get_window('hann', L) (sym=False), rounded to float32 as scipy.welch does
+        const double w = 0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)L);
+        h[n] = (float)w;
+        ss += (double)h[n] * (double)h[n];
+    }
+    CUDA_TRY(cudaMalloc(&pl->d_hann, L * sizeof(float)));
+    pl->dev_allocs.push_back(pl->d_hann);
+    CUDA_TRY(cudaMemcpy(pl->d_hann, h.data(), L * sizeof(float), cudaMemcpyHostToDevice));
+    pl->hann_sumsq = ss;
+    return RMX_OK;
+}
+
+extern "C" size_t rmx_welch_workspace_bytes(const rmx_plan* pl, int segments_in_flight) {
+    if (!pl || segments_in_flight <= 0) return 0;
+    const size_t L = size_t(1) << pl->logL;
+    return L * sizeof(float) + (size_t)segments_in_flight * L * sizeof(float2) + 512;
+}
+
+extern "C" int rmx_welch_psd(rmx_plan* pl, const uint8_t* iq, float* psd, double sample_rate, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+    if (!pl || !iq || !psd || !workspace) return fail(RMX_ERR_ARG, "null argument to rmx_welch_psd");
+    if (pl->n_samples != (1LL << pl->logL)) return fail(RMX_ERR_ARG, "Welch needs n_samples == fft_len (nperseg)");
+    if (!(sample_rate > 0)) return fail(RMX_ERR_ARG, "sample_rate must be positive");
+    int rc = ensure_hann(pl);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t L = size_t(1) << pl->logL;
+    const size_t accum_bytes = (L * sizeof(float) + 255) & ~size_t(255);
+    if (workspace_bytes < accum_bytes + L * sizeof(float2))
+        return fail(RMX_ERR_WORKSPACE, "Welch workspace too small: %zu bytes", workspace_bytes);
+    float* accum = reinterpret_cast<float*>(workspace);
+    float2* Y = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) + accum_bytes);
+    const int group = (int)std::min<size_t>((size_t)pl->n_signals, (workspace_bytes - accum_bytes) / (L * sizeof(float2)));
+    CUDA_TRY(cudaMemsetAsync(accum, 0, L * sizeof(float), st));
+    const int np = pl->n_passes;
+    const int logtile = kLogThreads + pl->loge;
+    for (int first = 0; first < pl->n_signals; first += group) {
+        const int cnt = std::min(group, pl->n_signals - first);
+        const uint8_t* in = iq + (size_t)first * 2 * L;
+        if (np == 1) {
+            const long long total = (long long)cnt << pl->logL;
+            k_unpack_window<<<grid_for(total, 256), 256, 0, st>>>(in, pl->d_hann, Y, pl->logL, total);
+            LAUNCH_CHECK("unpack_window");
+        } else {
+            PassParams pp = base_params(pl);
+            pp.n_items = cnt;
+            pp.cu8 = in;
+            pp.window = pl->d_hann;
+            pp.src = Y;
+            pp.dst = Y;
+            const unsigned grid = tiles_of(pl, cnt);
+            for (int t = 0; t < np - 1; ++t) {
+                pp.tabs = pl->tabs[t];
+                pp.logS = pl->logs[t];
+                rc = launch_pass(get_col_kernel(pl->logn[t], pl->loge, t == 0 ? K_FWD_CU8 : K_FWD), "welch_col_fwd",
+                                 dim3(grid), pp, st);
+                if (rc) return rc;
+            }
+        }
+        // last pass: FFT rows and accumulate |X|^2 over the group's segments
+        PassParams pp = base_params(pl);
+        pp.n_items = cnt;
+        pp.src = Y;
+        pp.accum = accum;
+        pp.tabs = pl->tabs[np - 1];
+        const KernelEntry k = get_contig_kernel(pl->logn[np - 1], pl->loge, C_FWD_PSD);
+        const unsigned tiles_per_sig = (unsigned)std::max<long long>(1, (1LL << pl->logL) >> logtile);
+        if ((1LL << pl->logL) < (1LL << logtile)) return fail(RMX_ERR_UNSUPPORTED, "Welch needs nperseg >= %d", 1 << logtile);
+        // enough CTAs to fill the GPU twice over; each accumulates a chunk of segments in registers
+        int chunks = std::max(1, std::min(cnt, (int)((148 * 4 + tiles_per_sig - 1) / tiles_per_sig)));
+        pp.items_per_cta = (cnt + chunks - 1) / chunks;
+        chunks = (cnt + pp.items_per_cta - 1) / pp.items_per_cta;
+        rc = launch_pass(k, "contig_fwd_psd", dim3(tiles_per_sig, chunks), pp, st);
+        if (rc) return rc;
+    }
+    // density scaling: 1 / (fs * sum(w^2)), averaged over the segments
+    const float scale = (float)(1.0 / (sample_rate * pl->hann_sumsq * (double)pl->n_signals));
+    k_psd_finalize<<<grid_for((long long)L, 256), 256, 0, st>>>(layout_of(pl), accum, psd, pl->logL, scale);
+    LAUNCH_CHECK("psd_finalize");
+    return RMX_OK;
+}
+
+__global__ void k_power_db(const float* __restrict__ in, float* __restrict__ out, size_t n, float eps) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = 10.0f * log10f(in[i] + eps);
+}
+
+extern "C" int rmx_power_db(const float* in, float* out, size_t n, float eps, void* stream) {
+    if (n == 0) return RMX_OK;
+    if (!in || !out) return fail(RMX_ERR_ARG, "null argument to rmx_power_db");
+    k_power_db<<<grid_for((long long)n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n, eps);
+    LAUNCH_CHECK("power_db");
+    return RMX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// peak candidates, mean/median, stats
+// ---------------------------------------------------------------------------------------
+// scipy.signal._peak_finding_utils._local_maxima_1d, one thread per rising edge.
+__global__ void __launch_bounds__(256) k_threshold_peaks(const float* __restrict__ x, int n, float height,
+                                                         int32_t* __restrict__ idx, int32_t* __restrict__ count, int cap) {
+    const int i_max = n - 1;
+    for (int i = 1 + blockIdx.x * blockDim.x + threadIdx.x; i < i_max; i += gridDim.x * blockDim.x) {
+        const float v = x[i];
+        if (!(x[i - 1] < v) || !(v >= height)) continue;
+        int ahead = i + 1;
+        while (ahead < i_max && x[ahead] == v) ++ahead;
+        if (x[ahead] < v) {
+            const int mid = (i + ahead - 1) / 2;
+            const int slot = atomicAdd(count, 1);
+            if (slot < cap) idx[slot] = mid;
+        }
+    }
+}
+
+extern "C" int rmx_threshold_peaks(const float* db, int n, float height, int32_t* idx, int32_t* count, int cap,
+                                   void* stream) {
+    if (!db || !idx || !count) return fail(RMX_ERR_ARG, "null argument to rmx_threshold_peaks");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
+    if (n < 3) return RMX_OK;
+    k_threshold_peaks<<<grid_for(n, 256), 256, 0, st>>>(db, n, height, idx, count, cap);
+    LAUNCH_CHECK("threshold_peaks");
+    return RMX_OK;
+}
+
+extern "C" int rmx_select_by_distance_host(const int32_t* pos, const float* heights, int n, int distance, uint8_t* keep) {
+    // find_peaks(distance=): visit peaks from the highest to the lowest; a kept peak removes every
+    // not-yet-visited neighbour closer than `distance` samples.  Ties in height are broken by
+    // position (later position = higher priority, as a stable argsort visited from the end does).
+    if (n <= 0) return RMX_OK;
+    if (!pos || !heights || !keep) return fail(RMX_ERR_ARG, "null argument to rmx_select_by_distance_host");
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return heights[a] < heights[b]; });
+    std::fill(keep, keep + n, (uint8_t)1);
+    for (int o = n - 1; o >= 0; --o) {
+        const int j = order[o];
+        if (!keep[j]) continue;
+        for (int k = j - 1; k >= 0 && pos[j] - pos[k] < distance; --k) keep[k] = 0;
+        for (int k = j + 1; k < n && pos[k] - pos[j] < distance; ++k) keep[k] = 0;
+    }
+    return RMX_OK;
+}
+
+__device__ __forceinline__ uint32_t float_order_key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// single CTA: mean (double) + radix-select of the two middle order statistics
+__global__ void __launch_bounds__(1024) k_mean_median(const float* __restrict__ x, int n, float* __restrict__ out) {
+    __shared__ unsigned hist[256];
+    __shared__ double s_sum[32];
+    __shared__ uint32_t s_prefix;
+    __shared__ unsigned s_rank;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)x[i];
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_sum[w];
+        out[0] = (float)(t / (double)n);
+    }
+    float med[2];
+    for (int which = 0; which < 2; ++which) {
+        const unsigned rank0 = which == 0 ? (unsigned)((n - 1) / 2) : (unsigned)(n / 2);
+        if (threadIdx.x == 0) { s_prefix = 0; s_rank = rank0; }
+        __syncthreads();
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            const uint32_t mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint32_t k = float_order_key(x[i]);
+                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xffu], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned r = s_rank, b = 0;
+                while (b < 255 && r >= hist[b]) { r -= hist[b]; ++b; }
+                s_rank = r;
+                s_prefix = prefix | (b << shift);
+            }
+            __syncthreads();
+        }
+        med[which] = key_to_float(s_prefix);
+        __syncthreads();
+    }
+    // np.median: mean of the two middle values (identical when n is odd)
+    if (threadIdx.x == 0) out[1] = (n & 1) ? med[0] : 0.5f * (med[0] + med[1]);
+}
+
+extern "C" int rmx_mean_median(const float* db, int n, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace; (void)workspace_bytes;
+    if (!db || !out) return fail(RMX_ERR_ARG, "null argument to rmx_mean_median");
+    if (n <= 0) return fail(RMX_ERR_ARG, "rmx_mean_median needs n > 0");
+    k_mean_median<<<1, 1024, 0, (cudaStream_t)stream>>>(db, n, out);
+    LAUNCH_CHECK("mean_median");
+    return RMX_OK;
+}
+
+// exact integer statistics: |x|^2 = ((2I-255)^2 + (2Q-255)^2) / 4
+__global__ void __launch_bounds__(256) k_signal_stats(const uint8_t* __restrict__ in, size_t n,
+                                                      unsigned long long* __restrict__ acc) {
+    unsigned long long sum = 0;
+    unsigned mx = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uchar2 b = reinterpret_cast<const uchar2*>(in)[i];
+        const int a = 2 * (int)b.x - 255, c = 2 * (int)b.y - 255;
+        const unsigned p = (unsigned)(a * a + c * c);
+        sum += p;
+        mx = max(mx, p);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&acc[0], sum);
+        atomicMax(reinterpret_cast<unsigned*>(&acc[1]), mx);
+    }
+}
+
+__global__ void k_signal_stats_final(const unsigned long long* __restrict__ acc, size_t n, rmx_stats* __restrict__ out) {
+    rmx_stats s;
+    s.mean_power = ((double)acc[0] / 4.0) / (double)n;
+    const unsigned mx = *reinterpret_cast<const unsigned*>(&acc[1]);
+    s.peak_amplitude = sqrtf((float)mx * 0.25f);
+    s.pad = 0.f;
+    *out = s;
+}
+
+extern "C" int rmx_signal_stats(const uint8_t* iq, size_t n_samples, rmx_stats* out, void* stream) {
+    if (!iq || !out) return fail(RMX_ERR_ARG, "null argument to rmx_signal_stats");
+    if (n_samples == 0) return fail(RMX_ERR_ARG, "rmx_signal_stats needs n_samples > 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    // the 16 accumulator bytes live in the output struct's storage until the final kernel overwrites it
+    static_assert(sizeof(rmx_stats) >= 2 * sizeof(unsigned long long), "rmx_stats too small for the accumulators");
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(out);
+    CUDA_TRY(cudaMemsetAsync(acc, 0, 2 * sizeof(unsigned long long), st));
+    k_signal_stats<<<grid_for((long long)n_samples, 256), 256, 0, st>>>(iq, n_samples, acc);
+    LAUNCH_CHECK("signal_stats");
+    k_signal_stats_final<<<1, 1, 0, st>>>(acc, n_samples, out);
+    LAUNCH_CHECK("signal_stats_final");
+    return RMX_OK;
+}

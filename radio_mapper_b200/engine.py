@@ -1,0 +1,252 @@
+"""Device-side engine: torch tensors in, librmx (hand-written sm_100a kernels) underneath.
+
+torch is used for device memory, streams and (elsewhere) torch.distributed — plumbing only.
+Every numeric stage runs in librmx.so through the C ABI of include/rmx.h.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native
+
+_lib = _native.load()
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: torch.Tensor):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _require_cuda(t: torch.Tensor, dtype, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise ValueError("%s must live on a CUDA device (the hot path has no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must have dtype %s (got %s)" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def next_pow2(n: int) -> int:
+    return 1 << max(0, int(n - 1).bit_length())
+
+
+def correlation_fft_len(n_samples: int) -> int:
+    """Smallest power of two >= 2N-1 (and >= 16): linear correlation without aliasing."""
+    return max(16, next_pow2(2 * int(n_samples) - 1))
+
+
+def pair_table(n: int) -> np.ndarray:
+    """All i<j in the enumeration order of tdoa_processor.py:156-157, int32[P, 2]."""
+    i, j = np.triu_indices(int(n), k=1)
+    return np.stack([i, j], axis=1).astype(np.int32)
+
+
+def unpack_cu8(iq_u8: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8[..., 2N] interleaved I,Q -> complex64[..., N], bit-exact with the reference unpack."""
+    _require_cuda(iq_u8, torch.uint8, "iq_u8")
+    if iq_u8.shape[-1] % 2:
+        raise ValueError("cu8 buffers hold an even number of bytes (I,Q pairs)")
+    n = iq_u8.numel() // 2
+    if out is None:
+        out = torch.empty(iq_u8.shape[:-1] + (iq_u8.shape[-1] // 2,), dtype=torch.complex64, device=iq_u8.device)
+    _require_cuda(out, torch.complex64, "out")
+    with torch.cuda.device(iq_u8.device):
+        _native.check(_lib.rmx_unpack_cu8(_ptr(iq_u8), _ptr(out), n, _stream_ptr()), "rmx_unpack_cu8")
+    return out
+
+
+class Plan:
+    """Batched FFT / correlation plan for `n_signals` signals of `n_samples` samples each,
+    zero-padded to `fft_len` (power of two)."""
+
+    def __init__(self, n_signals: int, n_samples: int, fft_len: Optional[int] = None, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("radio_mapper_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_signals = int(n_signals)
+        self.n_samples = int(n_samples)
+        self.fft_len = int(fft_len) if fft_len is not None else correlation_fft_len(n_samples)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _native.check(_lib.rmx_plan_create(ctypes.byref(self._h), self.n_signals, self.n_samples, self.fft_len, 0),
+                          "rmx_plan_create")
+        buf = (ctypes.c_int32 * 8)()
+        n = _native.check(_lib.rmx_plan_layout(self._h, buf, 8), "rmx_plan_layout")
+        self.pass_lengths = [int(buf[i]) for i in range(n)]
+        self._workspace: Optional[torch.Tensor] = None
+        self.max_lag: Optional[int] = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.rmx_plan_destroy(h)
+            except Exception:
+                pass
+
+    # ---- layout ------------------------------------------------------------------------
+    def layout_freq_index(self) -> np.ndarray:
+        """freq bin held at each position of the plan's spectrum layout (host, for tests/tools)."""
+        pos = np.arange(self.fft_len, dtype=np.int64)
+        freq = np.zeros(self.fft_len, dtype=np.int64)
+        weight, m = 1, self.fft_len
+        for n in self.pass_lengths:
+            s = m // n
+            freq += ((pos // s) % n) * weight
+            weight *= n
+            m = s
+        return freq
+
+    # ---- workspace -----------------------------------------------------------------------
+    def _get_workspace(self, nbytes: int) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = None
+            self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def workspace_bytes(self, n_pairs: int) -> int:
+        return int(_lib.rmx_plan_workspace_bytes(self._h, int(n_pairs)))
+
+    def set_max_lag(self, max_lag: Optional[int]):
+        self.max_lag = None if max_lag is None else int(max_lag)
+        _native.check(_lib.rmx_plan_set_max_lag(self._h, -1 if max_lag is None else int(max_lag)), "rmx_plan_set_max_lag")
+
+    # ---- stages --------------------------------------------------------------------------
+    def forward(self, iq_u8: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """cu8[n_signals, 2N] -> spectra complex64[n_signals, L] in the plan layout."""
+        _require_cuda(iq_u8, torch.uint8, "iq_u8")
+        if iq_u8.numel() != self.n_signals * 2 * self.n_samples:
+            raise ValueError("iq_u8 has %d bytes, plan expects %d x %d" % (iq_u8.numel(), self.n_signals, 2 * self.n_samples))
+        if out is None:
+            out = torch.empty((self.n_signals, self.fft_len), dtype=torch.complex64, device=self.device)
+        _require_cuda(out, torch.complex64, "out")
+        with torch.cuda.device(self.device):
+            _native.check(_lib.rmx_fft_forward_cu8(self._h, _ptr(iq_u8), _ptr(out), _stream_ptr()), "rmx_fft_forward_cu8")
+        return out
+
+    def spectrum_natural(self, spectra: torch.Tensor) -> torch.Tensor:
+        _require_cuda(spectra, torch.complex64, "spectra")
+        out = torch.empty_like(spectra)
+        n = spectra.numel() // self.fft_len
+        with torch.cuda.device(self.device):
+            _native.check(_lib.rmx_spectrum_natural(self._h, _ptr(spectra), _ptr(out), n, _stream_ptr()), "rmx_spectrum_natural")
+        return out
+
+    def spectrum_db(self, spectra: torch.Tensor, shift: bool = False) -> torch.Tensor:
+        _require_cuda(spectra, torch.complex64, "spectra")
+        n = spectra.numel() // self.fft_len
+        out = torch.empty((n, self.fft_len), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _native.check(_lib.rmx_spectrum_db(self._h, _ptr(spectra), _ptr(out), n, int(bool(shift)), _stream_ptr()),
+                          "rmx_spectrum_db")
+        return out
+
+    def xcorr_pairs_peak(self, spectra: torch.Tensor, pairs: torch.Tensor, out: Optional[torch.Tensor] = None,
+                         max_pairs_in_flight: Optional[int] = None) -> torch.Tensor:
+        """For each (i, j) row of `pairs` (int32[P, 2], device): peak of ifft(X_j conj X_i).
+
+        Returns int32[P, 4] records (lag, peak, frac, search value): use `peaks_to_numpy`."""
+        _require_cuda(spectra, torch.complex64, "spectra")
+        _require_cuda(pairs, torch.int32, "pairs")
+        if pairs.ndim != 2 or pairs.shape[1] != 2:
+            raise ValueError("pairs must be int32[P, 2]")
+        n_pairs = pairs.shape[0]
+        if out is None:
+            out = torch.empty((n_pairs, 4), dtype=torch.int32, device=self.device)
+        _require_cuda(out, torch.int32, "out")
+        if n_pairs == 0:
+            return out
+        chunk = n_pairs if max_pairs_in_flight is None else max(1, min(n_pairs, int(max_pairs_in_flight)))
+        ws = self._get_workspace(self.workspace_bytes(chunk))
+        with torch.cuda.device(self.device):
+            _native.check(_lib.rmx_xcorr_pairs_peak(self._h, _ptr(spectra), _ptr(pairs), n_pairs, _ptr(out), _ptr(ws),
+                                                    ws.numel(), _stream_ptr()), "rmx_xcorr_pairs_peak")
+        return out
+
+    def welch_psd(self, iq_u8: torch.Tensor, sample_rate: float, segments_in_flight: int = 64) -> torch.Tensor:
+        """Welch PSD of n_signals segments of nperseg = fft_len samples each (float32[L], natural order)."""
+        _require_cuda(iq_u8, torch.uint8, "iq_u8")
+        if self.n_samples != self.fft_len:
+            raise ValueError("Welch plans need n_samples == fft_len")
+        if iq_u8.numel() != self.n_signals * 2 * self.fft_len:
+            raise ValueError("iq_u8 has %d bytes, expected %d" % (iq_u8.numel(), self.n_signals * 2 * self.fft_len))
+        psd = torch.empty(self.fft_len, dtype=torch.float32, device=self.device)
+        nb = int(_lib.rmx_welch_workspace_bytes(self._h, max(1, min(self.n_signals, int(segments_in_flight)))))
+        ws = self._get_workspace(nb)
+        with torch.cuda.device(self.device):
+            _native.check(_lib.rmx_welch_psd(self._h, _ptr(iq_u8), _ptr(psd), float(sample_rate), _ptr(ws), nb, _stream_ptr()),
+                          "rmx_welch_psd")
+        return psd
+
+
+def peaks_to_numpy(records: torch.Tensor) -> np.ndarray:
+    """int32[P, 4] device records -> host structured array (lag, peak, frac, search)."""
+    host = records.detach().cpu().numpy()
+    return host.view(np.dtype([("lag", "<i4"), ("peak", "<f4"), ("frac", "<f4"), ("search", "<f4")])).reshape(-1)
+
+
+def power_db(p: torch.Tensor, eps: float = 1e-24) -> torch.Tensor:
+    _require_cuda(p, torch.float32, "p")
+    out = torch.empty_like(p)
+    with torch.cuda.device(p.device):
+        _native.check(_lib.rmx_power_db(_ptr(p), _ptr(out), p.numel(), float(eps), _stream_ptr()), "rmx_power_db")
+    return out
+
+
+def threshold_peaks(db: torch.Tensor, height: float, cap: Optional[int] = None) -> np.ndarray:
+    """Sorted bin indices of local maxima (scipy `_local_maxima_1d` semantics) with db >= height."""
+    _require_cuda(db, torch.float32, "db")
+    n = db.numel()
+    cap = n // 2 + 1 if cap is None else int(cap)
+    idx = torch.empty(max(cap, 1), dtype=torch.int32, device=db.device)
+    count = torch.zeros(1, dtype=torch.int32, device=db.device)
+    with torch.cuda.device(db.device):
+        _native.check(_lib.rmx_threshold_peaks(_ptr(db), n, float(height), _ptr(idx), _ptr(count), cap, _stream_ptr()),
+                      "rmx_threshold_peaks")
+    c = int(count.item())
+    if c > cap:
+        raise _native.RmxError("threshold_peaks: %d candidates exceed cap %d" % (c, cap))
+    return np.sort(idx[:c].cpu().numpy())
+
+
+def select_by_distance(positions: np.ndarray, heights: np.ndarray, distance: int) -> np.ndarray:
+    """find_peaks(distance=) greedy rule on host arrays; returns the kept positions."""
+    positions = np.ascontiguousarray(positions, dtype=np.int32)
+    heights = np.ascontiguousarray(heights, dtype=np.float32)
+    keep = np.ones(len(positions), dtype=np.uint8)
+    if len(positions):
+        _native.check(_lib.rmx_select_by_distance_host(positions.ctypes.data_as(ctypes.c_void_p),
+                                                       heights.ctypes.data_as(ctypes.c_void_p), len(positions),
+                                                       int(np.ceil(distance)), keep.ctypes.data_as(ctypes.c_void_p)),
+                      "rmx_select_by_distance_host")
+    return positions[keep.astype(bool)]
+
+
+def mean_median(db: torch.Tensor):
+    """(mean, median) of a float32 device vector as Python floats."""
+    _require_cuda(db, torch.float32, "db")
+    out = torch.empty(2, dtype=torch.float32, device=db.device)
+    with torch.cuda.device(db.device):
+        _native.check(_lib.rmx_mean_median(_ptr(db), db.numel(), _ptr(out), None, 0, _stream_ptr()), "rmx_mean_median")
+    m = out.cpu().numpy()
+    return np.float32(m[0]), np.float32(m[1])
+
+
+def signal_stats(iq_u8: torch.Tensor):
+    """(mean |x|^2 as float64, max |x| as float32) straight from the cu8 bytes."""
+    _require_cuda(iq_u8, torch.uint8, "iq_u8")
+    out = torch.empty(16, dtype=torch.uint8, device=iq_u8.device)
+    with torch.cuda.device(iq_u8.device):
+        _native.check(_lib.rmx_signal_stats(_ptr(iq_u8), iq_u8.numel() // 2, _ptr(out), _stream_ptr()), "rmx_signal_stats")
+    raw = out.cpu().numpy()
+    return float(raw[:8].view(np.float64)[0]), np.float32(raw[8:12].view(np.float32)[0])
