@@ -1,0 +1,330 @@
+#!/usr/bin/env python3
+"""Benchmark of the radio-mapper hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+A "step" is one pass of the hot path over one batch of synthetic cu8 IQ: for each of the
+workload's windows, fused unpack + forward FFT of all buoys, then conj-multiply + inverse FFT
++ arg-max/parabolic lag for all buoy pairs.  Metric (BASELINE.json): correlated
+pair-samples/s = pairs * samples_per_window * windows / time, whole job over all ranks.
+
+One JSON line is printed by rank 0 (see the contract in the task statement).  For N > 1 it is
+launched by torchrun, one rank per GPU; each rank processes its own windows (weak scaling)
+and the 16-byte peak records are all-gathered over NCCL inside the timed step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "correlated_pair_samples_per_sec"
+UNIT = "pair-samples/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[2] — the default single-GPU correlate workload
+    "cfg3": dict(desc="16 buoys (120 pairs), 2^22-sample windows, 5 windows (10.24 s @ 2.048 Msps) of synthetic cu8 IQ",
+                 buoys=16, samples=1 << 22, windows=5, fs=2_048_000),
+    # BASELINE.json configs[3]
+    "cfg4": dict(desc="64 buoys (2016 pairs), 2^20-sample windows, 4 windows per rank", buoys=64, samples=1 << 20,
+                 windows=4, fs=2_048_000),
+    # BASELINE.json configs[0]
+    "cfg1": dict(desc="3 buoys (3 pairs), 2.048 Msps, 1 s window", buoys=3, samples=2_048_000, windows=1, fs=2_048_000),
+    # BASELINE.json configs[4]
+    "cfg5": dict(desc="8 buoys (28 pairs), 2^26-sample windows", buoys=8, samples=1 << 26, windows=1, fs=2_048_000),
+    # small smoke-sized case
+    "tiny": dict(desc="4 buoys, 2^14-sample windows, 2 windows", buoys=4, samples=1 << 14, windows=2, fs=2_048_000),
+}
+
+
+def algorithmic_bytes(B, P, N, L):
+    """per window  B*(2N + 8L) + P*(16L + 16)."""
+    return B * (2 * N + 8 * L) + P * (16 * L + 16), B * (2 * N + 8 * L), P * (16 * L + 16)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_indices):
+        self.idx = set(int(i) for i in gpu_indices)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8 or not f[0].isdigit() or int(f[0]) not in self.idx:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------
+# CPU legs (the only places that may execute oracle/)
+# ----------------------------------------------------------------------------------------
+def cpu_sample_run(iq_sample, threads):
+    """Oracle (reference arithmetic) on uint8[b, 2N]: unpack + correlate + lag search for all
+    pairs of the sample.  Returns (seconds, n_pairs)."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    b = iq_sample.shape[0]
+    pairs = oracle.pair_list(b)
+    t0 = time.perf_counter()
+    x = [oracle.unpack_cu8(row) for row in iq_sample]
+
+    def one(pr):
+        c, lags = oracle.xcorr_full(x[pr[0]], x[pr[1]])
+        return oracle.peak_lag(c, lags)
+
+    if threads <= 1:
+        res = [one(p) for p in pairs]
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            res = list(ex.map(one, pairs))
+    return time.perf_counter() - t0, len(pairs), res
+
+
+def run_reference(args, wl):
+    """`--impl reference`: the reference's CPU arithmetic (oracle port: numpy unpack +
+    scipy.signal.correlate + argmax; the reference has no compiled implementation of this
+    path) on a bounded sample of the workload, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from radio_mapper_b200 import synth
+    N = wl["samples"]
+    cores = os.cpu_count() or 1
+    # bounded sample: one window, as many buoys as keep a step to a few seconds
+    b = min(wl["buoys"], 8 if N <= (1 << 22) else 3)
+    iq, _, _ = synth.delayed_buoys(4242, b, N, sample_rate=wl["fs"])
+    n_pairs = b * (b - 1) // 2
+    threads = max(1, min(cores, n_pairs))
+    for _ in range(args.warmup):
+        cpu_sample_run(iq, threads)
+    t_total = 0.0
+    for _ in range(args.steps):
+        t, _, _ = cpu_sample_run(iq, threads)
+        t_total += t
+    ps = n_pairs * N * args.steps / t_total
+    sample = "one window, first %d buoys (%d pairs) of the workload per step" % (b, n_pairs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (complex64 numpy/scipy)", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": wl["desc"], "buoys": wl["buoys"], "samples_per_window": N,
+                   "sample": sample},
+        "cpu_baseline": {"value": ps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "host_cpus": cores},
+        "e2e": {"value": ps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------
+def run_b200(args, wl):
+    import torch
+    import torch.distributed as dist
+    from radio_mapper_b200 import sharding, synth
+    from radio_mapper_b200.tdoa_processor import TDoAProcessor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    B, N, W, fs = wl["buoys"], wl["samples"], wl["windows"], wl["fs"]
+    P = B * (B - 1) // 2
+
+    # synthetic input, resident in HBM (device-timed arm) and in pinned host memory (e2e arm)
+    iq_dev, delays = synth.delayed_buoys_torch(1000 * 3 + rank, B, W, N, device, sample_rate=fs)
+    proc = TDoAProcessor()
+    buoy_ids = ["BUOY_%02d" % b for b in range(B)]
+    cor = proc._correlator(B, N, device)
+    plan = cor.plan
+    L = plan.fft_len
+    windows = list(range(W))
+
+    def step():
+        rec, en = cor.run_device(iq_dev, windows)
+        if world > 1:
+            rec, en = sharding.gather_records(rec, en, W * world, P, world, rank)
+        return rec, en
+
+    for _ in range(max(args.warmup, 3)):
+        rec, en = step()
+    torch.cuda.synchronize()
+
+    # correctness guard on the timed configuration: lags must equal the generator's delays
+    got = rec[:W].cpu().numpy()[..., 0] if world == 1 else rec[rank * W:(rank + 1) * W].cpu().numpy()[..., 0]
+    want = np.stack([delays[:, j] - delays[:, i] for i, j in cor.pairs_host], axis=1)
+    if not np.array_equal(got, want):
+        raise SystemExit("bench: lags do not match the synthetic delays (%d mismatches)" % int((got != want).sum()))
+
+    sampler = ClockSampler(range(world) if rank == 0 else [])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    plan.profile(True)
+    cor.launches = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = cor.launches
+    prof = plan.profile_collect()
+    plan.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = P * N * W * world * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public API: pinned host cu8 -> TDoAMeasurement list ----------
+    iq_host = torch.empty(iq_dev.shape, dtype=torch.uint8, pin_memory=True)
+    iq_host.copy_(iq_dev)
+    torch.cuda.synchronize()
+    for _ in range(2):
+        meas = proc.correlate_iq(iq_host, buoy_ids, fs, 121.5)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        meas = proc.correlate_iq(iq_host, buoy_ids, fs, 121.5)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    assert len(meas) == W * P
+    e2e_value = P * N * W * world * args.steps / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant stage (fused correlate + peak) -------------------------------
+    peak, peak_src = measured_peak()
+    total_b, fwd_b, pair_b = algorithmic_bytes(B, P, N, L)
+    pair_names = [k for k in prof if k.startswith(("contig_inv", "col_inv", "finalize"))]
+    fwd_names = [k for k in prof if k not in pair_names]
+    pair_ms = sum(prof[k][1] for k in pair_names)
+    fwd_ms = sum(prof[k][1] for k in fwd_names)
+    n_calls = args.steps * W                               # one correlate call per window
+    pair_gbs = pair_b * n_calls / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else 0.0
+    whole_gbs = total_b * W * args.steps / (elapsed_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "correlate+peak stage (" + " + ".join(sorted(pair_names)) + ")",
+        "achieved": pair_gbs, "peak": peak, "unit": "GB/s", "frac": pair_gbs / peak, "traffic": None,
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": pair_b,
+        "avg_launch_ms": pair_ms / max(1, n_calls), "share_of_step": pair_ms / max(1e-9, pair_ms + fwd_ms),
+        "whole_step": {"achieved": whole_gbs, "frac": whole_gbs / peak, "algorithmic_bytes_per_window": total_b},
+        "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items())},
+    }
+
+    # ---- CPU baseline: the oracle on a bounded sample, this box's host cores ---------------------
+    b = 4 if N <= (1 << 22) else 2
+    sample_iq = iq_host[:b, 0, :].numpy()
+    t_cpu, n_cpu_pairs, cpu_res = cpu_sample_run(sample_iq, 1)
+    cpu_lags = [r[0] for r in cpu_res]
+    import oracle
+    gpu_lags = [int(want[0][k]) for k, (i, j) in enumerate(cor.pairs_host) if i < b and j < b]
+    cpu_baseline = {"value": n_cpu_pairs * N / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                    "sample": "window 0, first %d buoys (%d pairs): numpy unpack + scipy.signal.correlate + argmax, %.1f s"
+                              % (b, n_cpu_pairs, t_cpu),
+                    "host_cpus": os.cpu_count(), "lags_match_gpu": cpu_lags == gpu_lags}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (complex64)", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": wl["desc"], "buoys": B, "pairs": P, "samples_per_window": N,
+                   "fft_len": L, "windows_per_step_per_gpu": W, "passes": plan.pass_lengths,
+                   "l2": "inputs larger than L2 (%.1f GB of spectra+workspace touched per window)" % (total_b / 1e9),
+                   "sharding": "windows across ranks; NCCL all_gather of peak records" if world > 1 else "single GPU"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(iq_host.numel()),
+                "d2h_bytes_per_step": int(W * P * 16 + W * B * 8), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "api": "TDoAProcessor.correlate_iq(pinned host uint8[B,W,2N]) -> List[TDoAMeasurement]"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("RMX_WORKLOAD", "cfg3"), choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_b200(args, wl)
+
+
+if __name__ == "__main__":
+    main()

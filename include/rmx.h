@@ -83,9 +83,11 @@ RMX_API size_t rmx_plan_workspace_bytes(const rmx_plan* plan, int n_pairs);
 RMX_API int rmx_plan_set_max_lag(rmx_plan* plan, long long max_lag);
 
 /* Stages 1+2 — fused unpack + zero-pad + batched forward FFT of all signals.
- * iq: uint8[n_signals][2*n_samples]; spectra: complex64[n_signals][fft_len] (plan layout).
+ * iq: signal s starts at iq + s*signal_stride_bytes (0 = densely packed, 2*n_samples) and holds
+ * 2*n_samples bytes; spectra: complex64[n_signals][fft_len] (plan layout).
  * replaces fft(iq_samples) of buoy_node.py:401 / iq_stream_client.py:187 / signal_analyzer.py:63 */
-RMX_API int rmx_fft_forward_cu8(const rmx_plan* plan, const uint8_t* iq, rmx_complex64* spectra, void* stream);
+RMX_API int rmx_fft_forward_cu8(const rmx_plan* plan, const uint8_t* iq, size_t signal_stride_bytes,
+                                rmx_complex64* spectra, void* stream);
 
 /* plan layout -> natural bin order (out may not alias in) */
 RMX_API int rmx_spectrum_natural(const rmx_plan* plan, const rmx_complex64* spectra, rmx_complex64* out,
@@ -130,8 +132,24 @@ RMX_API int rmx_select_by_distance_host(const int32_t* positions, const float* h
  * replaces np.mean(...) signal_analyzer.py:75 and np.median(...) buoy_node.py:427 */
 RMX_API int rmx_mean_median(const float* db, int n, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Per-launch timing with CUDA events on the launching stream (off by default).  enable != 0 clears
+ * earlier records and starts recording; collect synchronises the recorded events and returns the
+ * number of distinct kernel names written to out[0..cap). */
+typedef struct rmx_prof_entry {
+    char name[32];
+    int32_t launches;
+    float total_ms;
+} rmx_prof_entry;
+RMX_API int rmx_profile_enable(rmx_plan* plan, int enable);
+RMX_API int rmx_profile_collect(rmx_plan* plan, rmx_prof_entry* out, int cap);
+
 /* signal statistics straight from cu8 (signal_analyzer.py:92-99); out: device rmx_stats */
 RMX_API int rmx_signal_stats(const uint8_t* iq, size_t n_samples, rmx_stats* out, void* stream);
+
+/* Exact per-signal energy for normalising correlation peaks: out[s] = sum_n (2I-255)^2 + (2Q-255)^2
+ * = 4 * sum |x_s[n]|^2 (unpack of buoy_node.py:392-398 in integers).  out: device uint64[n_signals]. */
+RMX_API int rmx_signal_energy(const uint8_t* iq, size_t signal_stride_bytes, int n_signals, size_t n_samples,
+                              unsigned long long* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,9 @@ SIGNATURES = {
     "rmx_plan_layout": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_int32), c_int]),
     "rmx_plan_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "rmx_plan_set_max_lag": (c_int, [c_void_p, c_longlong]),
-    "rmx_fft_forward_cu8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rmx_fft_forward_cu8": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "rmx_profile_enable": (c_int, [c_void_p, c_int]),
+    "rmx_profile_collect": (c_int, [c_void_p, c_void_p, c_int]),
     "rmx_spectrum_natural": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "rmx_xcorr_pairs_peak": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rmx_spectrum_db": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
@@ -33,6 +35,7 @@ SIGNATURES = {
     "rmx_select_by_distance_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "rmx_mean_median": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rmx_signal_stats": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
+    "rmx_signal_energy": (c_int, [c_void_p, c_size_t, c_int, c_size_t, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,116 @@
+"""Batched multi-buoy correlator: the device-side half of `TDoAProcessor.correlate_iq`.
+
+One `Correlator` serves a fixed (n_buoys, n_samples) shape on one GPU.  Per window it runs
+    rmx_fft_forward_cu8   (fused cu8 unpack + zero-pad + forward FFT of all buoys)
+    rmx_signal_energy     (exact per-buoy energy, for the coherence / confidence value)
+    rmx_xcorr_pairs_peak  (conj-multiply + inverse FFT + arg-max + parabolic, all pairs)
+and brings back only the 16-byte peak records.  Multi-GPU: windows (or, with fewer windows
+than ranks, pairs) are sharded over the ranks of the default torch.distributed group; each
+rank recomputes the spectra it needs and only peak records cross NVLink (one all_gather).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native, engine, sharding
+
+_lib = _native.load()
+
+RECORD_DTYPE = np.dtype([("lag", "<i4"), ("peak", "<f4"), ("frac", "<f4"), ("coherence", "<f4")])
+
+
+def as_u8_tensor(iq_u8) -> torch.Tensor:
+    if isinstance(iq_u8, np.ndarray):
+        if iq_u8.dtype != np.uint8:
+            raise TypeError("cu8 IQ must be uint8")
+        return torch.from_numpy(np.ascontiguousarray(iq_u8))
+    if not isinstance(iq_u8, torch.Tensor) or iq_u8.dtype != torch.uint8:
+        raise TypeError("cu8 IQ must be a uint8 numpy array or torch tensor")
+    return iq_u8
+
+
+class Correlator:
+    def __init__(self, n_buoys: int, n_samples: int, device=None, workspace_pairs: Optional[int] = None):
+        if n_buoys < 2:
+            raise ValueError("need at least two buoys to correlate")
+        self.n_buoys, self.n_samples = int(n_buoys), int(n_samples)
+        self.plan = engine.Plan(self.n_buoys, self.n_samples, device=device)
+        self.device = self.plan.device
+        self.pairs_host = engine.pair_table(self.n_buoys)
+        self.pairs = torch.from_numpy(self.pairs_host).to(self.device)
+        self.n_pairs = len(self.pairs_host)
+        self.spectra = torch.empty((self.n_buoys, self.plan.fft_len), dtype=torch.complex64, device=self.device)
+        self.workspace_pairs = workspace_pairs
+        self._staging: Optional[torch.Tensor] = None
+        self.launches = 0            # kernels launched by the last run()
+
+    # -- device-resident core ---------------------------------------------------------------
+    def run_device(self, iq_dev: torch.Tensor, windows, pair_slice: Optional[slice] = None,
+                   records: Optional[torch.Tensor] = None, energy: Optional[torch.Tensor] = None):
+        """iq_dev: CUDA uint8[B, W, 2N].  Processes the listed windows; returns (records int32
+        [len(windows), P', 4], energy uint64[len(windows), B]) on the device."""
+        pairs = self.pairs if pair_slice is None else self.pairs[pair_slice].contiguous()
+        nw = len(windows)
+        if records is None:
+            records = torch.empty((nw, pairs.shape[0], 4), dtype=torch.int32, device=self.device)
+        if energy is None:
+            energy = torch.empty((nw, self.n_buoys), dtype=torch.int64, device=self.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        n_passes = len(self.plan.pass_lengths)
+        for k, w in enumerate(windows):
+            view = iq_dev[:, w, :]
+            self.plan.forward(view, out=self.spectra)
+            _native.check(_lib.rmx_signal_energy(ctypes.c_void_p(view.data_ptr()), view.stride(0) if self.n_buoys > 1 else 0,
+                                                 self.n_buoys, self.n_samples, ctypes.c_void_p(energy[k].data_ptr()), stream),
+                          "rmx_signal_energy")
+            self.plan.xcorr_pairs_peak(self.spectra, pairs, out=records[k], max_pairs_in_flight=self.workspace_pairs)
+            self.launches += n_passes + 1 + n_passes + 1
+        return records, energy
+
+    # -- host-facing call ---------------------------------------------------------------------
+    def run(self, iq_u8: torch.Tensor, max_lag: Optional[int] = None, distributed: bool = False) -> np.ndarray:
+        """iq_u8: uint8[B, W, 2N] on the host (pinned for async copies) or on the device.
+        Returns host records [W, P] (RECORD_DTYPE)."""
+        if iq_u8.shape[0] != self.n_buoys or iq_u8.shape[2] != 2 * self.n_samples:
+            raise ValueError("expected uint8[%d, W, %d], got %s" % (self.n_buoys, 2 * self.n_samples, tuple(iq_u8.shape)))
+        n_windows = iq_u8.shape[1]
+        if max_lag != self.plan.max_lag:
+            self.plan.set_max_lag(max_lag)
+        self.launches = 0
+        world, rank = sharding.world_and_rank() if distributed else (1, 0)
+        windows, pair_slice = sharding.shard_units(n_windows, self.n_pairs, world, rank)
+        with torch.cuda.device(self.device):
+            if iq_u8.is_cuda:
+                iq_dev = iq_u8
+            else:
+                if self._staging is None or self._staging.shape != iq_u8.shape:
+                    self._staging = torch.empty(iq_u8.shape, dtype=torch.uint8, device=self.device)
+                if len(windows) == n_windows:
+                    self._staging.copy_(iq_u8, non_blocking=True)
+                else:
+                    for w in windows:                      # copy only this rank's windows
+                        self._staging[:, w, :].copy_(iq_u8[:, w, :], non_blocking=True)
+                iq_dev = self._staging
+            rec_dev, en_dev = self.run_device(iq_dev, windows, pair_slice)
+            if world > 1:
+                rec_dev, en_dev = sharding.gather_records(rec_dev, en_dev, n_windows, self.n_pairs, world, rank)
+            rec = rec_dev.cpu().numpy()
+            en = en_dev.cpu().numpy()
+        return self._finish(rec, en)
+
+    def _finish(self, rec: np.ndarray, energy_x4: np.ndarray) -> np.ndarray:
+        out = np.empty(rec.shape[:2], dtype=RECORD_DTYPE)
+        out["lag"] = rec[..., 0]
+        out["peak"] = rec[..., 1].view(np.float32)
+        out["frac"] = rec[..., 2].view(np.float32)
+        e = energy_x4.astype(np.float64) / 4.0                                  # sum |x|^2 per (window, buoy)
+        pi, pj = self.pairs_host[:, 0], self.pairs_host[:, 1]
+        denom = np.sqrt(e[:, pi] * e[:, pj])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            coh = np.where(denom > 0, out["peak"].astype(np.float64) / denom, 0.0)
+        out["coherence"] = np.clip(coh, 0.0, 1.0).astype(np.float32)
+        return out

@@ -22,7 +22,10 @@ static KernelEntry col_by_logn(int logn) {
     }
 }
 
+KernelEntry get_col_kernel32(int logn, int mode);   // rmx_inst_col32.cu
+
 KernelEntry get_col_kernel(int logn, int loge, int mode) {
+    if (loge == 5) return get_col_kernel32(logn, mode);
     if (loge != 4) return KernelEntry{nullptr, 0, 0};
     switch (mode) {
         case K_FWD_CU8: return col_by_logn<4, K_FWD_CU8>(logn);

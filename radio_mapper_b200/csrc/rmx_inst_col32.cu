@@ -1,0 +1,32 @@
+// Instantiations of the column-pass kernels with 32 elements per thread (n = 32, 512, 1024).
+#include "rmx_dispatch.h"
+
+namespace rmx {
+
+template <int LOGN, int MODE>
+static KernelEntry col32_entry() {
+    using GEO = TileGeom<LOGN, 5, true>;
+    return KernelEntry{(PassKernel)k_col<LOGN, 5, MODE>, GEO::SMEM_BYTES, GEO::LOGG};
+}
+
+template <int MODE>
+static KernelEntry col32_by_logn(int logn) {
+    switch (logn) {
+        case 5: return col32_entry<5, MODE>();
+        case 9: return col32_entry<9, MODE>();
+        case 10: return col32_entry<10, MODE>();
+        default: return KernelEntry{nullptr, 0, 0};
+    }
+}
+
+KernelEntry get_col_kernel32(int logn, int mode) {
+    switch (mode) {
+        case K_FWD_CU8: return col32_by_logn<K_FWD_CU8>(logn);
+        case K_FWD: return col32_by_logn<K_FWD>(logn);
+        case K_INV: return col32_by_logn<K_INV>(logn);
+        case K_INV_ARGMAX: return col32_by_logn<K_INV_ARGMAX>(logn);
+        default: return KernelEntry{nullptr, 0, 0};
+    }
+}
+
+}  // namespace rmx

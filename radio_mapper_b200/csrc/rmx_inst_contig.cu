@@ -25,7 +25,10 @@ static KernelEntry contig_by_logn(int logn) {
     }
 }
 
+KernelEntry get_contig_kernel32(int logn, int mode);   // rmx_inst_contig32.cu
+
 KernelEntry get_contig_kernel(int logn, int loge, int mode) {
+    if (loge == 5) return get_contig_kernel32(logn, mode);
     if (loge != 4) return KernelEntry{nullptr, 0, 0};
     switch (mode) {
         case C_FWD: return contig_by_logn<4, C_FWD>(logn);

@@ -1,0 +1,23 @@
+// Instantiations of the contiguous-pass kernels with 32 elements per thread (n = 8192).
+#include "rmx_dispatch.h"
+
+namespace rmx {
+
+template <int MODE>
+static KernelEntry contig32_entry() {
+    using GEO = TileGeom<13, 5, false>;
+    return KernelEntry{(PassKernel)k_contig<13, 5, MODE>, GEO::SMEM_BYTES, GEO::LOGG};
+}
+
+KernelEntry get_contig_kernel32(int logn, int mode) {
+    if (logn != 13) return KernelEntry{nullptr, 0, 0};
+    switch (mode) {
+        case C_FWD: return contig32_entry<C_FWD>();
+        case C_FWD_CU8: return contig32_entry<C_FWD_CU8>();
+        case C_INV_PAIR: return contig32_entry<C_INV_PAIR>();
+        case C_FWD_PSD: return contig32_entry<C_FWD_PSD>();
+        default: return KernelEntry{nullptr, 0, 0};
+    }
+}
+
+}  // namespace rmx

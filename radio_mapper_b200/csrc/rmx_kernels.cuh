@@ -21,8 +21,8 @@
 namespace rmx {
 
 struct Partial {
-    float val;     // |c|^2 of the best lag in this tile (-1 = none)
-    int32_t lag;   // signed lag
+    float val;      // |c|^2 of the best lag in this tile (-1 = none)
+    uint32_t rank;  // lag + lag_neg_max (position in the lag-ordered 'full' output); lowest wins ties
 };
 
 struct PassParams {
@@ -56,34 +56,38 @@ __device__ __forceinline__ float2 load_cu8_sample(const uint8_t* base, long long
     return make_float2((float)b.x - 127.5f, (float)b.y - 127.5f);
 }
 
-__device__ __forceinline__ bool better(float v, int lag, float bv, int blag) {
+__device__ __forceinline__ bool better(float v, uint32_t rank, float bv, uint32_t brank) {
     // np.argmax semantics on the lag-ordered 'full' output: first (lowest-lag) maximum wins
-    return v > bv || (v == bv && lag < blag);
+    return v > bv || (v == bv && rank < brank);
 }
 
-// Block-wide arg-max of (val, lag); result valid in thread 0.
-__device__ __forceinline__ void block_argmax(float& v, int& lag) {
+// Block-wide arg-max.  Every thread passes its best value `v` (-1 if none) and a functor that
+// returns the lowest rank among the thread's elements equal to a given value.  The common path
+// costs one float max-reduction; only threads holding the block maximum evaluate ranks.
+// Result valid in thread 0.
+template <class RankOf>
+__device__ __forceinline__ void block_argmax(float& v, uint32_t& rank, RankOf rank_of) {
     __shared__ float s_v[kThreads / 32];
-    __shared__ int s_l[kThreads / 32];
+    __shared__ float s_max;
+    __shared__ unsigned s_rank;
+    float m = v;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, v, off);
-        const int ol = __shfl_xor_sync(0xffffffffu, lag, off);
-        if (better(ov, ol, v, lag)) { v = ov; lag = ol; }
-    }
-    const int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) { s_v[w] = v; s_l[w] = lag; }
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) s_v[threadIdx.x >> 5] = m;
+    if (threadIdx.x == 0) s_rank = 0xffffffffu;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        v = threadIdx.x < kThreads / 32 ? s_v[threadIdx.x] : -1.f;
-        lag = threadIdx.x < kThreads / 32 ? s_l[threadIdx.x] : 0x7fffffff;
+    if (threadIdx.x == 0) {
+        float t = s_v[0];
 #pragma unroll
-        for (int off = 4; off > 0; off >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, v, off);
-            const int ol = __shfl_xor_sync(0xffffffffu, lag, off);
-            if (better(ov, ol, v, lag)) { v = ov; lag = ol; }
-        }
+        for (int w = 1; w < kThreads / 32; ++w) t = fmaxf(t, s_v[w]);
+        s_max = t;
     }
+    __syncthreads();
+    const float bm = s_max;
+    if (v == bm && bm >= 0.f) atomicMin(&s_rank, rank_of(bm));
+    __syncthreads();
+    v = bm;
+    rank = s_rank;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -237,26 +241,34 @@ __global__ void __launch_bounds__(kThreads) k_col(const PassParams p) {
     }
 
     if constexpr (MODE == K_INV_ARGMAX) {
-        // pass 0 of the inverse: row m1, column j  ->  lag index m = m1*s + j (natural order)
-        const long long Lfull = 1LL << p.logL;
+        // pass 0 of the inverse: row m1, column j  ->  lag index m = m1*s + j (natural order).
+        // rank = (m + lag_neg_max) mod L orders the lags like scipy's 'full' output; a lag is
+        // searched iff rank <= lag_pos_max + lag_neg_max.
+        const uint32_t lmask = (1u << p.logL) - 1u;
+        const uint32_t span = (uint32_t)p.lag_pos_max + (uint32_t)p.lag_neg_max;
+        const uint32_t rank0 = ((uint32_t)base + ((uint32_t)i0 << logS) + (uint32_t)p.lag_neg_max) & lmask;
+        const uint32_t rstep = (uint32_t)NT << logS;
+        float v[E];
         float bv = -1.f;
-        int blag = 0x7fffffff;
 #pragma unroll
         for (int u = 0; u < E; ++u) {
-            const long long m = base + ((long long)(i0 + u * NT) << logS);
-            int lag;
-            bool ok;
-            if (m <= p.lag_pos_max) { lag = (int)m; ok = true; }
-            else { lag = (int)(m - Lfull); ok = (m - Lfull) >= -(long long)p.lag_neg_max; }
-            const float v = cnorm2(r[u]);
-            if (ok && better(v, lag, bv, blag)) { bv = v; blag = lag; }
+            const uint32_t rank = (rank0 + (uint32_t)u * rstep) & lmask;
+            v[u] = rank <= span ? cnorm2(r[u]) : -1.f;
+            bv = fmaxf(bv, v[u]);
         }
         if constexpr (GEO::NSTAGES > 1) __syncthreads();
-        block_argmax(bv, blag);
+        uint32_t brank;
+        block_argmax(bv, brank, [&](float target) {
+            uint32_t best = 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < E; ++u)
+                if (v[u] == target) best = min(best, (rank0 + (uint32_t)u * rstep) & lmask);
+            return best;
+        });
         if (threadIdx.x == 0) {
             Partial out;
             out.val = bv;
-            out.lag = blag;
+            out.rank = brank;
             p.partials[(item << log_tpb) + jt] = out;
         }
     } else {

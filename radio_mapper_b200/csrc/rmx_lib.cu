@@ -47,12 +47,20 @@ extern "C" int rmx_version(void) { return RMX_VERSION; }
 // ---------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------
+struct ProfRecord {
+    const char* name;
+    cudaEvent_t start, stop;
+};
+
 struct rmx_plan {
+    bool prof_enabled = false;
+    std::vector<ProfRecord> prof_records;      // one per launch since rmx_profile_enable
+    std::vector<cudaEvent_t> prof_pool;        // recycled events
     int n_signals = 0;
     long long n_samples = 0;
     int logL = 0;
-    int loge = 4;
     int n_passes = 0;
+    int loge[kMaxStages + 2] = {0};   // pass t register-tile size (elements per thread, log2)
     int logn[kMaxStages + 2] = {0};   // pass t transform length
     int logs[kMaxStages + 2] = {0};   // pass t column stride (0 for the contiguous pass)
     StageTables tabs[kMaxStages + 2];
@@ -87,14 +95,31 @@ static int build_stage_tables(rmx_plan* pl, int logn, int loge, StageTables* out
     return RMX_OK;
 }
 
+// register-tile size (log2 elements per thread) for a pass of length 2^logn: fewest Stockham
+// stages first, then the smaller register footprint
+static int choose_col_loge(int logn) {
+    const bool ok16 = logn >= 4 && logn <= max_col_logn(4);
+    const bool ok32 = logn >= 5 && logn <= max_col_logn(5) && get_col_kernel(logn, 5, K_FWD).fn != nullptr;
+    if (ok16 && ok32) return ((logn + 4) / 5 < (logn + 3) / 4) ? 5 : 4;
+    if (ok16) return 4;
+    if (ok32) return 5;
+    return 0;
+}
+static int choose_contig_loge(int logn) {
+    if (logn >= 4 && logn <= max_contig_logn(4)) return 4;
+    if (logn == max_contig_logn(5)) return 5;
+    return 0;
+}
+
 static int choose_passes(rmx_plan* pl) {
-    const int loge = pl->loge, logL = pl->logL;
-    const int maxc = max_contig_logn(loge), maxk = max_col_logn(loge), minn = min_logn(loge);
+    const int logL = pl->logL;
+    const int maxc = max_contig_logn(5), maxk = max_col_logn(5), minn = 4;
     if (logL < minn) return fail(RMX_ERR_UNSUPPORTED, "fft_len 2^%d is below the minimum 2^%d", logL, minn);
     if (logL <= maxc) {
         pl->n_passes = 1;
         pl->logn[0] = logL;
         pl->logs[0] = 0;
+        pl->loge[0] = choose_contig_loge(logL);
         return RMX_OK;
     }
     const int contig = std::min(maxc, logL - minn);
@@ -106,12 +131,14 @@ static int choose_passes(rmx_plan* pl) {
         // smaller transforms first: the outermost pass then has the most columns per tile
         const int a = rem / (ncol - t);
         pl->logn[t] = a;
+        pl->loge[t] = choose_col_loge(a);
         stride -= a;
         pl->logs[t] = stride;
         rem -= a;
-        if (a < minn || a > maxk) return fail(RMX_ERR_UNSUPPORTED, "no pass split for fft_len 2^%d", logL);
+        if (pl->loge[t] == 0) return fail(RMX_ERR_UNSUPPORTED, "no pass split for fft_len 2^%d", logL);
     }
     pl->logn[ncol] = contig;
+    pl->loge[ncol] = choose_contig_loge(contig);
     pl->logs[ncol] = 0;
     pl->n_passes = ncol + 1;
     return RMX_OK;
@@ -131,7 +158,7 @@ extern "C" int rmx_plan_create(rmx_plan** out, int n_signals, size_t n_samples, 
     pl->logL = 0;
     while ((size_t(1) << pl->logL) < fft_len) ++pl->logL;
     int rc = choose_passes(pl);
-    for (int t = 0; rc == RMX_OK && t < pl->n_passes; ++t) rc = build_stage_tables(pl, pl->logn[t], pl->loge, &pl->tabs[t]);
+    for (int t = 0; rc == RMX_OK && t < pl->n_passes; ++t) rc = build_stage_tables(pl, pl->logn[t], pl->loge[t], &pl->tabs[t]);
     if (rc != RMX_OK) {
         rmx_plan_destroy(pl);
         return rc;
@@ -144,6 +171,8 @@ extern "C" int rmx_plan_create(rmx_plan** out, int n_signals, size_t n_samples, 
 extern "C" int rmx_plan_destroy(rmx_plan* pl) {
     if (!pl) return RMX_OK;
     for (void* p : pl->dev_allocs) cudaFree(p);
+    for (auto& r : pl->prof_records) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
+    for (auto e : pl->prof_pool) cudaEventDestroy(e);
     delete pl;
     return RMX_OK;
 }
@@ -169,7 +198,7 @@ extern "C" int rmx_plan_set_max_lag(rmx_plan* pl, long long max_lag) {
 static int tiles_per_item_pass0(const rmx_plan* pl) {
     // arg-max partials produced per pair by the outermost inverse pass
     if (pl->n_passes == 1) return 1;
-    const int logG = kLogThreads + pl->loge - pl->logn[0];
+    const int logG = kLogThreads + pl->loge[0] - pl->logn[0];
     return 1 << (pl->logs[0] - logG);
 }
 
@@ -180,13 +209,67 @@ extern "C" size_t rmx_plan_workspace_bytes(const rmx_plan* pl, int n_pairs) {
 }
 
 // ---------------------------------------------------------------------------------------
+// per-launch profiling (CUDA events on the launching stream; off by default)
+// ---------------------------------------------------------------------------------------
+struct ProfScope {
+    rmx_plan* pl;
+    cudaStream_t st;
+    cudaEvent_t stop = nullptr;
+    ProfScope(const rmx_plan* plan, const char* name, cudaStream_t stream) : pl(const_cast<rmx_plan*>(plan)), st(stream) {
+        if (!pl || !pl->prof_enabled) { pl = nullptr; return; }
+        cudaEvent_t ev[2];
+        for (int i = 0; i < 2; ++i) {
+            if (!pl->prof_pool.empty()) { ev[i] = pl->prof_pool.back(); pl->prof_pool.pop_back(); }
+            else if (cudaEventCreate(&ev[i]) != cudaSuccess) { pl = nullptr; return; }
+        }
+        pl->prof_records.push_back(ProfRecord{name, ev[0], ev[1]});
+        stop = ev[1];
+        cudaEventRecord(ev[0], st);
+    }
+    ~ProfScope() { if (pl) cudaEventRecord(stop, st); }
+};
+
+extern "C" int rmx_profile_enable(rmx_plan* pl, int enable) {
+    if (!pl) return fail(RMX_ERR_ARG, "plan is null");
+    for (auto& r : pl->prof_records) { pl->prof_pool.push_back(r.start); pl->prof_pool.push_back(r.stop); }
+    pl->prof_records.clear();
+    pl->prof_enabled = enable != 0;
+    return RMX_OK;
+}
+
+extern "C" int rmx_profile_collect(rmx_plan* pl, rmx_prof_entry* out, int cap) {
+    if (!pl || (!out && cap > 0)) return fail(RMX_ERR_ARG, "null argument to rmx_profile_collect");
+    int n = 0;
+    for (auto& r : pl->prof_records) {
+        CUDA_TRY(cudaEventSynchronize(r.stop));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, r.start, r.stop));
+        int k = 0;
+        while (k < n && strncmp(out[k].name, r.name, sizeof(out[k].name)) != 0) ++k;
+        if (k == n) {
+            if (n >= cap) continue;
+            memset(&out[n], 0, sizeof(out[n]));
+            strncpy(out[n].name, r.name, sizeof(out[n].name) - 1);
+            ++n;
+        }
+        out[k].launches += 1;
+        out[k].total_ms += ms;
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------
 // pass launchers
 // ---------------------------------------------------------------------------------------
-static int launch_pass(const KernelEntry& k, const char* name, dim3 grid, const PassParams& pp, cudaStream_t st) {
+static int launch_pass(const rmx_plan* pl, const KernelEntry& k, const char* name, dim3 grid, const PassParams& pp,
+                       cudaStream_t st) {
     if (!k.fn) return fail(RMX_ERR_UNSUPPORTED, "kernel %s is not instantiated for this size", name);
     if (k.smem_bytes > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute((const void*)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem_bytes));
-    k.fn<<<grid, kThreads, k.smem_bytes, st>>>(pp);
+    {
+        ProfScope prof(pl, name, st);
+        k.fn<<<grid, kThreads, k.smem_bytes, st>>>(pp);
+    }
     LAUNCH_CHECK(name);
     return RMX_OK;
 }
@@ -204,42 +287,48 @@ static PassParams base_params(const rmx_plan* pl) {
     return pp;
 }
 
-static unsigned tiles_of(const rmx_plan* pl, long long n_items) {
-    const int logtile = kLogThreads + pl->loge;
+static unsigned tiles_of(const rmx_plan* pl, int pass, long long n_items) {
+    const int logtile = kLogThreads + pl->loge[pass];
     const long long total = n_items << pl->logL;
     return (unsigned)((total + (1LL << logtile) - 1) >> logtile);
 }
 
 // forward FFT of n_items signals from cu8 (optionally windowed) into `spectra`
-static int forward_cu8(const rmx_plan* pl, const uint8_t* iq, float2* spectra, int n_items, const float* window,
-                       cudaStream_t st) {
+static int forward_cu8(const rmx_plan* pl, const uint8_t* iq, long long stride_bytes, float2* spectra, int n_items,
+                       const float* window, cudaStream_t st) {
     const int np = pl->n_passes;
     PassParams pp = base_params(pl);
+    if (stride_bytes > 0) pp.cu8_stride = stride_bytes;
     pp.n_items = n_items;
     pp.cu8 = iq;
     pp.window = window;
     pp.dst = spectra;
     pp.src = spectra;
-    const unsigned grid = tiles_of(pl, n_items);
     if (np == 1) {
         if (window) return fail(RMX_ERR_UNSUPPORTED, "windowed single-pass forward is handled by the caller");
         pp.tabs = pl->tabs[0];
-        return launch_pass(get_contig_kernel(pl->logn[0], pl->loge, C_FWD_CU8), "contig_fwd_cu8", dim3(grid), pp, st);
+        return launch_pass(pl, get_contig_kernel(pl->logn[0], pl->loge[0], C_FWD_CU8), "contig_fwd_cu8",
+                           dim3(tiles_of(pl, 0, n_items)), pp, st);
     }
     for (int t = 0; t < np - 1; ++t) {
         pp.tabs = pl->tabs[t];
         pp.logS = pl->logs[t];
-        int rc = launch_pass(get_col_kernel(pl->logn[t], pl->loge, t == 0 ? K_FWD_CU8 : K_FWD),
-                             t == 0 ? "col_fwd_cu8" : "col_fwd", dim3(grid), pp, st);
+        int rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], t == 0 ? K_FWD_CU8 : K_FWD),
+                             t == 0 ? "col_fwd_cu8" : "col_fwd", dim3(tiles_of(pl, t, n_items)), pp, st);
         if (rc) return rc;
     }
     pp.tabs = pl->tabs[np - 1];
-    return launch_pass(get_contig_kernel(pl->logn[np - 1], pl->loge, C_FWD), "contig_fwd", dim3(grid), pp, st);
+    return launch_pass(pl, get_contig_kernel(pl->logn[np - 1], pl->loge[np - 1], C_FWD), "contig_fwd",
+                       dim3(tiles_of(pl, np - 1, n_items)), pp, st);
 }
 
-extern "C" int rmx_fft_forward_cu8(const rmx_plan* pl, const uint8_t* iq, rmx_complex64* spectra, void* stream) {
+extern "C" int rmx_fft_forward_cu8(const rmx_plan* pl, const uint8_t* iq, size_t signal_stride_bytes,
+                                   rmx_complex64* spectra, void* stream) {
     if (!pl || !iq || !spectra) return fail(RMX_ERR_ARG, "null argument to rmx_fft_forward_cu8");
-    return forward_cu8(pl, iq, reinterpret_cast<float2*>(spectra), pl->n_signals, nullptr, (cudaStream_t)stream);
+    if (signal_stride_bytes != 0 && (signal_stride_bytes < (size_t)(2 * pl->n_samples) || (signal_stride_bytes & 1)))
+        return fail(RMX_ERR_ARG, "signal_stride_bytes must be even and >= 2*n_samples (got %zu)", signal_stride_bytes);
+    return forward_cu8(pl, iq, (long long)signal_stride_bytes, reinterpret_cast<float2*>(spectra), pl->n_signals, nullptr,
+                       (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -272,25 +361,26 @@ __global__ void __launch_bounds__(128) k_finalize_sum(const Partial* __restrict_
                                                       const float2* __restrict__ D, int logL, int logn0, int logs0,
                                                       int lag_pos_max, int lag_neg_max, rmx_peak* __restrict__ out) {
     __shared__ float s_v[4];
-    __shared__ int s_l[4];
+    __shared__ uint32_t s_l[4];
     __shared__ float2 s_sum[4];
     const int item = blockIdx.x;
     float bv = -1.f;
-    int blag = 0x7fffffff;
+    uint32_t brank = 0xffffffffu;
     for (int t = threadIdx.x; t < tiles_per_item; t += blockDim.x) {
         const Partial p = partials[(long long)item * tiles_per_item + t];
-        if (p.val >= 0.f && better(p.val, p.lag, bv, blag)) { bv = p.val; blag = p.lag; }
+        if (p.val >= 0.f && better(p.val, p.rank, bv, brank)) { bv = p.val; brank = p.rank; }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-        const int ol = __shfl_xor_sync(0xffffffffu, blag, off);
-        if (better(ov, ol, bv, blag)) { bv = ov; blag = ol; }
+        const uint32_t ol = __shfl_xor_sync(0xffffffffu, brank, off);
+        if (better(ov, ol, bv, brank)) { bv = ov; brank = ol; }
     }
-    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_l[threadIdx.x >> 5] = blag; }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_l[threadIdx.x >> 5] = brank; }
     __syncthreads();
-    bv = s_v[0]; blag = s_l[0];
-    for (int w = 1; w < 4; ++w) if (better(s_v[w], s_l[w], bv, blag)) { bv = s_v[w]; blag = s_l[w]; }
+    bv = s_v[0]; brank = s_l[0];
+    for (int w = 1; w < 4; ++w) if (better(s_v[w], s_l[w], bv, brank)) { bv = s_v[w]; brank = s_l[w]; }
+    const int blag = (int)brank - lag_neg_max;
 
     const long long L = 1LL << logL;
     const int n0 = 1 << logn0;
@@ -328,31 +418,30 @@ __global__ void __launch_bounds__(128) k_finalize_sum(const Partial* __restrict_
 __global__ void __launch_bounds__(128) k_finalize_direct(const float2* __restrict__ C, int logL, int lag_pos_max,
                                                          int lag_neg_max, rmx_peak* __restrict__ out) {
     __shared__ float s_v[4];
-    __shared__ int s_l[4];
+    __shared__ uint32_t s_l[4];
     const int item = blockIdx.x;
     const long long L = 1LL << logL;
     const float2* __restrict__ c = C + ((long long)item << logL);
     float bv = -1.f;
-    int blag = 0x7fffffff;
+    uint32_t brank = 0xffffffffu;
+    const uint32_t span = (uint32_t)lag_pos_max + (uint32_t)lag_neg_max;
     for (long long m = threadIdx.x; m < L; m += blockDim.x) {
-        int lag;
-        bool ok;
-        if (m <= lag_pos_max) { lag = (int)m; ok = true; }
-        else { lag = (int)(m - L); ok = (m - L) >= -(long long)lag_neg_max; }
+        const uint32_t rank = (uint32_t)((m + lag_neg_max) & (L - 1));
         const float v = cnorm2(c[m]);
-        if (ok && better(v, lag, bv, blag)) { bv = v; blag = lag; }
+        if (rank <= span && better(v, rank, bv, brank)) { bv = v; brank = rank; }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-        const int ol = __shfl_xor_sync(0xffffffffu, blag, off);
-        if (better(ov, ol, bv, blag)) { bv = ov; blag = ol; }
+        const uint32_t ol = __shfl_xor_sync(0xffffffffu, brank, off);
+        if (better(ov, ol, bv, brank)) { bv = ov; brank = ol; }
     }
-    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_l[threadIdx.x >> 5] = blag; }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_l[threadIdx.x >> 5] = brank; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        bv = s_v[0]; blag = s_l[0];
-        for (int w = 1; w < 4; ++w) if (better(s_v[w], s_l[w], bv, blag)) { bv = s_v[w]; blag = s_l[w]; }
+        bv = s_v[0]; brank = s_l[0];
+        for (int w = 1; w < 4; ++w) if (better(s_v[w], s_l[w], bv, brank)) { bv = s_v[w]; brank = s_l[w]; }
+        const int blag = (int)brank - lag_neg_max;
         float y[3];
         for (int d = -1; d <= 1; ++d) {
             const long long lag = (long long)blag + d;
@@ -396,24 +485,30 @@ extern "C" int rmx_xcorr_pairs_peak(const rmx_plan* pl, const rmx_complex64* spe
         pp.dst = D;
         pp.partials = partials;
         pp.scale = 1.0f / (float)L;
-        const unsigned grid = tiles_of(pl, cnt);
         // innermost pass first: rows of X_j * conj(X_i)
         pp.tabs = pl->tabs[np - 1];
-        int rc = launch_pass(get_contig_kernel(pl->logn[np - 1], pl->loge, C_INV_PAIR), "contig_inv_pair", dim3(grid), pp, st);
+        int rc = launch_pass(pl, get_contig_kernel(pl->logn[np - 1], pl->loge[np - 1], C_INV_PAIR), "contig_inv_pair",
+                             dim3(tiles_of(pl, np - 1, cnt)), pp, st);
         if (rc) return rc;
         for (int t = np - 2; t >= 0; --t) {
             pp.tabs = pl->tabs[t];
             pp.logS = pl->logs[t];
-            rc = launch_pass(get_col_kernel(pl->logn[t], pl->loge, t == 0 ? K_INV_ARGMAX : K_INV),
-                             t == 0 ? "col_inv_argmax" : "col_inv", dim3(grid), pp, st);
+            rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], t == 0 ? K_INV_ARGMAX : K_INV),
+                             t == 0 ? "col_inv_argmax" : "col_inv", dim3(tiles_of(pl, t, cnt)), pp, st);
             if (rc) return rc;
         }
         if (np == 1) {
-            k_finalize_direct<<<cnt, 128, 0, st>>>(D, pl->logL, (int)pl->lag_pos_max, (int)pl->lag_neg_max, out + first);
+            {
+                ProfScope prof(pl, "finalize_direct", st);
+                k_finalize_direct<<<cnt, 128, 0, st>>>(D, pl->logL, (int)pl->lag_pos_max, (int)pl->lag_neg_max, out + first);
+            }
             LAUNCH_CHECK("finalize_direct");
         } else {
-            k_finalize_sum<<<cnt, 128, 0, st>>>(partials, tpi, D, pl->logL, pl->logn[0], pl->logs[0],
-                                                (int)pl->lag_pos_max, (int)pl->lag_neg_max, out + first);
+            {
+                ProfScope prof(pl, "finalize_sum", st);
+                k_finalize_sum<<<cnt, 128, 0, st>>>(partials, tpi, D, pl->logL, pl->logn[0], pl->logs[0],
+                                                    (int)pl->lag_pos_max, (int)pl->lag_neg_max, out + first);
+            }
             LAUNCH_CHECK("finalize_sum");
         }
     }
@@ -599,7 +694,7 @@ extern "C" int rmx_welch_psd(rmx_plan* pl, const uint8_t* iq, float* psd, double
     const int group = (int)std::min<size_t>((size_t)pl->n_signals, (workspace_bytes - accum_bytes) / (L * sizeof(float2)));
     CUDA_TRY(cudaMemsetAsync(accum, 0, L * sizeof(float), st));
     const int np = pl->n_passes;
-    const int logtile = kLogThreads + pl->loge;
+    const int logtile = kLogThreads + pl->loge[np - 1];
     for (int first = 0; first < pl->n_signals; first += group) {
         const int cnt = std::min(group, pl->n_signals - first);
         const uint8_t* in = iq + (size_t)first * 2 * L;
@@ -614,12 +709,11 @@ extern "C" int rmx_welch_psd(rmx_plan* pl, const uint8_t* iq, float* psd, double
             pp.window = pl->d_hann;
             pp.src = Y;
             pp.dst = Y;
-            const unsigned grid = tiles_of(pl, cnt);
             for (int t = 0; t < np - 1; ++t) {
                 pp.tabs = pl->tabs[t];
                 pp.logS = pl->logs[t];
-                rc = launch_pass(get_col_kernel(pl->logn[t], pl->loge, t == 0 ? K_FWD_CU8 : K_FWD), "welch_col_fwd",
-                                 dim3(grid), pp, st);
+                rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], t == 0 ? K_FWD_CU8 : K_FWD), "welch_col_fwd",
+                                 dim3(tiles_of(pl, t, cnt)), pp, st);
                 if (rc) return rc;
             }
         }
@@ -629,14 +723,14 @@ extern "C" int rmx_welch_psd(rmx_plan* pl, const uint8_t* iq, float* psd, double
         pp.src = Y;
         pp.accum = accum;
         pp.tabs = pl->tabs[np - 1];
-        const KernelEntry k = get_contig_kernel(pl->logn[np - 1], pl->loge, C_FWD_PSD);
+        const KernelEntry k = get_contig_kernel(pl->logn[np - 1], pl->loge[np - 1], C_FWD_PSD);
         const unsigned tiles_per_sig = (unsigned)std::max<long long>(1, (1LL << pl->logL) >> logtile);
         if ((1LL << pl->logL) < (1LL << logtile)) return fail(RMX_ERR_UNSUPPORTED, "Welch needs nperseg >= %d", 1 << logtile);
         // enough CTAs to fill the GPU twice over; each accumulates a chunk of segments in registers
         int chunks = std::max(1, std::min(cnt, (int)((148 * 4 + tiles_per_sig - 1) / tiles_per_sig)));
         pp.items_per_cta = (cnt + chunks - 1) / chunks;
         chunks = (cnt + pp.items_per_cta - 1) / pp.items_per_cta;
-        rc = launch_pass(k, "contig_fwd_psd", dim3(tiles_per_sig, chunks), pp, st);
+        rc = launch_pass(pl, k, "contig_fwd_psd", dim3(tiles_per_sig, chunks), pp, st);
         if (rc) return rc;
     }
     // density scaling: 1 / (fs * sum(w^2)), averaged over the segments
@@ -801,6 +895,55 @@ __global__ void k_signal_stats_final(const unsigned long long* __restrict__ acc,
     s.peak_amplitude = sqrtf((float)mx * 0.25f);
     s.pad = 0.f;
     *out = s;
+}
+
+// per-signal exact energy: sum over samples of (2I-255)^2 + (2Q-255)^2  ( = 4 * sum |x|^2 )
+__global__ void __launch_bounds__(256) k_signal_energy(const uint8_t* __restrict__ in, size_t stride_bytes, size_t n,
+                                                       unsigned long long* __restrict__ out) {
+    const uint8_t* __restrict__ base = in + (size_t)blockIdx.y * stride_bytes;
+    unsigned long long sum = 0;
+    const bool vec = ((uintptr_t)base % 16 == 0);
+    if (vec) {
+        const uint4* __restrict__ b4 = reinterpret_cast<const uint4*>(base);
+        const size_t nvec = n / 8;
+        for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+            const uint4 w = __ldg(b4 + v);
+            const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+            unsigned part = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int a = 2 * (int)((ws[k] >> (8 * b)) & 0xffu) - 255;
+                    part += (unsigned)(a * a);
+                }
+            sum += part;
+        }
+        for (size_t i = nvec * 8 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+            const int a = 2 * (int)base[2 * i] - 255, c = 2 * (int)base[2 * i + 1] - 255;
+            sum += (unsigned)(a * a + c * c);
+        }
+    } else {
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+            const int a = 2 * (int)base[2 * i] - 255, c = 2 * (int)base[2 * i + 1] - 255;
+            sum += (unsigned)(a * a + c * c);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&out[blockIdx.y], sum);
+}
+
+extern "C" int rmx_signal_energy(const uint8_t* iq, size_t signal_stride_bytes, int n_signals, size_t n_samples,
+                                 unsigned long long* out, void* stream) {
+    if (!iq || !out) return fail(RMX_ERR_ARG, "null argument to rmx_signal_energy");
+    if (n_signals <= 0 || n_samples == 0) return fail(RMX_ERR_ARG, "rmx_signal_energy needs positive sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (signal_stride_bytes == 0) signal_stride_bytes = 2 * n_samples;
+    CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)n_signals * sizeof(unsigned long long), st));
+    const unsigned bx = (unsigned)std::max<long long>(1, std::min<long long>((long long)(n_samples / 8 + 255) / 256, 296 / std::max(1, std::min(n_signals, 296)) + 1));
+    k_signal_energy<<<dim3(bx, n_signals), 256, 0, st>>>(iq, signal_stride_bytes, n_samples, out);
+    LAUNCH_CHECK("signal_energy");
+    return RMX_OK;
 }
 
 extern "C" int rmx_signal_stats(const uint8_t* iq, size_t n_samples, rmx_stats* out, void* stream) {

@@ -123,16 +123,36 @@ class Plan:
 
     # ---- stages --------------------------------------------------------------------------
     def forward(self, iq_u8: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """cu8[n_signals, 2N] -> spectra complex64[n_signals, L] in the plan layout."""
-        _require_cuda(iq_u8, torch.uint8, "iq_u8")
-        if iq_u8.numel() != self.n_signals * 2 * self.n_samples:
-            raise ValueError("iq_u8 has %d bytes, plan expects %d x %d" % (iq_u8.numel(), self.n_signals, 2 * self.n_samples))
+        """cu8[n_signals, 2N] -> spectra complex64[n_signals, L] in the plan layout.
+
+        `iq_u8` may be a row-strided view (stride(0) >= 2N bytes, stride(1) == 1), e.g. one
+        window cut out of a [buoy, stream] buffer."""
+        if not isinstance(iq_u8, torch.Tensor) or not iq_u8.is_cuda or iq_u8.dtype != torch.uint8:
+            raise TypeError("iq_u8 must be a CUDA uint8 tensor (the hot path has no CPU fallback)")
+        if iq_u8.ndim != 2 or iq_u8.shape[0] != self.n_signals or iq_u8.shape[1] != 2 * self.n_samples:
+            raise ValueError("iq_u8 must be uint8[%d, %d] (got %s)" % (self.n_signals, 2 * self.n_samples, tuple(iq_u8.shape)))
+        if iq_u8.stride(1) != 1 or (self.n_signals > 1 and (iq_u8.stride(0) < 2 * self.n_samples or iq_u8.stride(0) % 2)):
+            raise ValueError("iq_u8 rows must be contiguous with an even row stride")
+        stride = iq_u8.stride(0) if self.n_signals > 1 else 0
         if out is None:
             out = torch.empty((self.n_signals, self.fft_len), dtype=torch.complex64, device=self.device)
         _require_cuda(out, torch.complex64, "out")
         with torch.cuda.device(self.device):
-            _native.check(_lib.rmx_fft_forward_cu8(self._h, _ptr(iq_u8), _ptr(out), _stream_ptr()), "rmx_fft_forward_cu8")
+            _native.check(_lib.rmx_fft_forward_cu8(self._h, _ptr(iq_u8), stride, _ptr(out), _stream_ptr()),
+                          "rmx_fft_forward_cu8")
         return out
+
+    # ---- profiling -----------------------------------------------------------------------
+    def profile(self, enable: bool = True):
+        _native.check(_lib.rmx_profile_enable(self._h, int(bool(enable))), "rmx_profile_enable")
+
+    def profile_collect(self):
+        """{kernel name: (launches, total_ms)} since profile(True); synchronises the recorded events."""
+        class _Entry(ctypes.Structure):
+            _fields_ = [("name", ctypes.c_char * 32), ("launches", ctypes.c_int32), ("total_ms", ctypes.c_float)]
+        buf = (_Entry * 32)()
+        n = _native.check(_lib.rmx_profile_collect(self._h, ctypes.cast(buf, ctypes.c_void_p), 32), "rmx_profile_collect")
+        return {buf[i].name.decode(): (int(buf[i].launches), float(buf[i].total_ms)) for i in range(n)}
 
     def spectrum_natural(self, spectra: torch.Tensor) -> torch.Tensor:
         _require_cuda(spectra, torch.complex64, "spectra")

@@ -110,3 +110,39 @@ def welch_stream(seed, n_segments, nperseg, sample_rate=2_400_000, n_tones=5):
         x = x / np.sqrt(1.0 + np.sum((10.0 ** (snrs / 20.0)) ** 2) / nperseg)
         out[2 * start:2 * (start + m)] = quantize_cu8(x, 20.0)
     return out, bins
+
+
+def delayed_buoys_torch(seed, n_buoys, n_windows, n_samples, device, sample_rate=2_048_000,
+                        bandwidth_hz=200_000.0, snr_db=10.0, max_delay=342):
+    """GPU-side generator for full-size bench inputs (not bit-identical to `delayed_buoys`).
+
+    Returns (iq_u8 CUDA uint8[B, W, 2N], delays int64[W, B]).  torch.fft is used here only to
+    shape the synthetic source; it is data generation, not the product path.
+    """
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    pad = max_delay + 2
+    total = n_samples + 2 * pad
+    out = torch.empty((n_buoys, n_windows, 2 * n_samples), dtype=torch.uint8, device=device)
+    delays = torch.randint(-max_delay, max_delay + 1, (n_windows, n_buoys), generator=g, device=device)
+    delays_h = delays.cpu()
+    freqs = torch.fft.fftfreq(total, 1.0 / sample_rate, device=device)
+    keep = (freqs.abs() <= bandwidth_hz / 2)
+    noise_amp = 10.0 ** (-snr_db / 20.0)
+    scale = RMS_LSB / (2.0 ** 0.5)
+    for w in range(n_windows):
+        spec = torch.randn(total, 2, generator=g, device=device)
+        spec = torch.view_as_complex(spec) * keep
+        s = torch.fft.ifft(spec)
+        s = s / s.abs().pow(2).mean().sqrt()
+        for b in range(n_buoys):
+            start = pad - int(delays_h[w, b])
+            gain = 0.7 + 0.3 * float(torch.rand(1, generator=g, device=device))
+            nz = torch.view_as_complex(torch.randn(n_samples, 2, generator=g, device=device)) * (noise_amp / 2.0 ** 0.5)
+            x = gain * s[start:start + n_samples] + nz
+            x = x / x.abs().pow(2).mean().sqrt()
+            q = torch.view_as_real(x).mul(scale).add(127.5).round().clamp_(0, 255).to(torch.uint8)
+            out[b, w] = q.reshape(-1)
+        del spec, s
+    return out, delays_h.numpy()
