@@ -89,6 +89,12 @@ RMX_API int rmx_plan_set_max_lag(rmx_plan* plan, long long max_lag);
 RMX_API int rmx_fft_forward_cu8(const rmx_plan* plan, const uint8_t* iq, size_t signal_stride_bytes,
                                 rmx_complex64* spectra, void* stream);
 
+/* Same transform for signals that are already complex64 (signal s at x + s*signal_stride_elems,
+ * 0 = densely packed); used where the reference hands complex samples around
+ * (signal_analyzer.py:47 analyze_spectrum, iq_stream_client.py:181 detect_signals). */
+RMX_API int rmx_fft_forward_c64(const rmx_plan* plan, const rmx_complex64* x, size_t signal_stride_elems,
+                                rmx_complex64* spectra, void* stream);
+
 /* plan layout -> natural bin order (out may not alias in) */
 RMX_API int rmx_spectrum_natural(const rmx_plan* plan, const rmx_complex64* spectra, rmx_complex64* out,
                          int n_signals, void* stream);
@@ -100,6 +106,22 @@ RMX_API int rmx_spectrum_natural(const rmx_plan* plan, const rmx_complex64* spec
  * :166; this produces the time difference that line computes) */
 RMX_API int rmx_xcorr_pairs_peak(const rmx_plan* plan, const rmx_complex64* spectra, const rmx_pair* pairs,
                          int n_pairs, rmx_peak* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Full correlation instead of its peak: out[p][m] = ifft(X_j conj X_i)[m], natural order
+ * (lag = m for m < L/2, m - L otherwise).  out: complex64[n_pairs][fft_len]. */
+RMX_API int rmx_xcorr_full(const rmx_plan* plan, const rmx_complex64* spectra, const rmx_pair* pairs, int n_pairs,
+                           rmx_complex64* out, void* stream);
+
+/* Arbitrary-length DFT (the reference FFTs whole captures of any length, signal_analyzer.py:62-63)
+ * by Bluestein's chirp-z on top of the power-of-two engine:
+ *   prepare: a[i] = x[i]*w[i] (i < n, else 0), chirp_circ[m] = w[min(m, padded_len-m)] for |m| < n,
+ *            w[i] = exp(-i*pi*i^2/n);  then conv = ifft(fft(a) * conj(fft(chirp_circ)))  (rmx_xcorr_full)
+ *   finish : X[k] = w[k]*conv[k], k < n. */
+RMX_API int rmx_bluestein_prepare(const rmx_complex64* x, size_t n, size_t padded_len, rmx_complex64* a,
+                                  rmx_complex64* chirp_circ, void* stream);
+RMX_API int rmx_bluestein_finish(const rmx_complex64* conv, size_t n, rmx_complex64* out, void* stream);
+/* out[k'] = 20*log10(|x[k]| + 1e-12) on a natural-order vector; shift != 0: k' = (k + n/2) mod n */
+RMX_API int rmx_abs_db(const rmx_complex64* x, size_t n, float* out_db, int shift, void* stream);
 
 /* Stage 5a — dB spectrum in natural order: out[k] = 20*log10(|X[k]| + 1e-12); shift != 0 applies
  * fftshift.  replaces buoy_node.py:405, iq_stream_client.py:191, signal_analyzer.py:64-67 */
@@ -145,6 +167,10 @@ RMX_API int rmx_profile_collect(rmx_plan* plan, rmx_prof_entry* out, int cap);
 
 /* signal statistics straight from cu8 (signal_analyzer.py:92-99); out: device rmx_stats */
 RMX_API int rmx_signal_stats(const uint8_t* iq, size_t n_samples, rmx_stats* out, void* stream);
+
+/* same statistics for complex64 samples (calculate_signal_stats, signal_analyzer.py:88);
+ * workspace: 16 bytes of device scratch */
+RMX_API int rmx_signal_stats_c64(const rmx_complex64* x, size_t n_samples, rmx_stats* out, void* workspace, void* stream);
 
 /* Exact per-signal energy for normalising correlation peaks: out[s] = sum_n (2I-255)^2 + (2Q-255)^2
  * = 4 * sum |x_s[n]|^2 (unpack of buoy_node.py:392-398 in integers).  out: device uint64[n_signals]. */

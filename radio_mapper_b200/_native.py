@@ -23,6 +23,12 @@ SIGNATURES = {
     "rmx_plan_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "rmx_plan_set_max_lag": (c_int, [c_void_p, c_longlong]),
     "rmx_fft_forward_cu8": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "rmx_fft_forward_c64": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "rmx_signal_stats_c64": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "rmx_xcorr_full": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "rmx_bluestein_prepare": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "rmx_bluestein_finish": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
+    "rmx_abs_db": (c_int, [c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
     "rmx_profile_enable": (c_int, [c_void_p, c_int]),
     "rmx_profile_collect": (c_int, [c_void_p, c_void_p, c_int]),
     "rmx_spectrum_natural": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

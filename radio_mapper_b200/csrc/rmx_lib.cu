@@ -258,6 +258,11 @@ extern "C" int rmx_profile_collect(rmx_plan* pl, rmx_prof_entry* out, int cap) {
     return n;
 }
 
+static unsigned grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    return (unsigned)std::max<long long>(1, std::min<long long>(g, 148LL * 16));
+}
+
 // ---------------------------------------------------------------------------------------
 // pass launchers
 // ---------------------------------------------------------------------------------------
@@ -329,6 +334,35 @@ extern "C" int rmx_fft_forward_cu8(const rmx_plan* pl, const uint8_t* iq, size_t
         return fail(RMX_ERR_ARG, "signal_stride_bytes must be even and >= 2*n_samples (got %zu)", signal_stride_bytes);
     return forward_cu8(pl, iq, (long long)signal_stride_bytes, reinterpret_cast<float2*>(spectra), pl->n_signals, nullptr,
                        (cudaStream_t)stream);
+}
+
+// forward FFT of complex64 signals (zero-padded into `spectra`, then transformed in place)
+extern "C" int rmx_fft_forward_c64(const rmx_plan* pl, const rmx_complex64* x, size_t signal_stride_elems,
+                                   rmx_complex64* spectra, void* stream) {
+    if (!pl || !x || !spectra) return fail(RMX_ERR_ARG, "null argument to rmx_fft_forward_c64");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t L = size_t(1) << pl->logL, N = (size_t)pl->n_samples;
+    if (signal_stride_elems == 0) signal_stride_elems = N;
+    if (signal_stride_elems < N) return fail(RMX_ERR_ARG, "signal_stride_elems must be >= n_samples");
+    CUDA_TRY(cudaMemcpy2DAsync(spectra, L * sizeof(float2), x, signal_stride_elems * sizeof(float2), N * sizeof(float2),
+                               (size_t)pl->n_signals, cudaMemcpyDeviceToDevice, st));
+    if (N < L)
+        CUDA_TRY(cudaMemset2DAsync(reinterpret_cast<float2*>(spectra) + N, L * sizeof(float2), 0, (L - N) * sizeof(float2),
+                                   (size_t)pl->n_signals, st));
+    const int np = pl->n_passes;
+    PassParams pp = base_params(pl);
+    pp.n_items = pl->n_signals;
+    pp.src = reinterpret_cast<const float2*>(spectra);
+    pp.dst = reinterpret_cast<float2*>(spectra);
+    for (int t = 0; t < np - 1; ++t) {
+        pp.tabs = pl->tabs[t];
+        pp.logS = pl->logs[t];
+        int rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], K_FWD), "col_fwd", dim3(tiles_of(pl, t, pl->n_signals)), pp, st);
+        if (rc) return rc;
+    }
+    pp.tabs = pl->tabs[np - 1];
+    return launch_pass(pl, get_contig_kernel(pl->logn[np - 1], pl->loge[np - 1], C_FWD), "contig_fwd",
+                       dim3(tiles_of(pl, np - 1, pl->n_signals)), pp, st);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -515,6 +549,107 @@ extern "C" int rmx_xcorr_pairs_peak(const rmx_plan* pl, const rmx_complex64* spe
     return RMX_OK;
 }
 
+// full correlation output: out[p][m] = ifft(X_j conj X_i)[m], natural order, m = lag mod L
+extern "C" int rmx_xcorr_full(const rmx_plan* pl, const rmx_complex64* spectra, const rmx_pair* pairs, int n_pairs,
+                              rmx_complex64* out, void* stream) {
+    if (!pl || !spectra || !pairs || !out) return fail(RMX_ERR_ARG, "null argument to rmx_xcorr_full");
+    if (n_pairs <= 0) return RMX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int np = pl->n_passes;
+    PassParams pp = base_params(pl);
+    pp.n_items = n_pairs;
+    pp.spectra = reinterpret_cast<const float2*>(spectra);
+    pp.pairs = reinterpret_cast<const int2*>(pairs);
+    pp.src = reinterpret_cast<const float2*>(out);
+    pp.dst = reinterpret_cast<float2*>(out);
+    pp.scale = 1.0f / (float)(size_t(1) << pl->logL);
+    pp.tabs = pl->tabs[np - 1];
+    int rc = launch_pass(pl, get_contig_kernel(pl->logn[np - 1], pl->loge[np - 1], C_INV_PAIR), "contig_inv_pair",
+                         dim3(tiles_of(pl, np - 1, n_pairs)), pp, st);
+    for (int t = np - 2; rc == RMX_OK && t >= 0; --t) {
+        pp.tabs = pl->tabs[t];
+        pp.logS = pl->logs[t];
+        rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], K_INV), "col_inv", dim3(tiles_of(pl, t, n_pairs)), pp, st);
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// Bluestein helpers (arbitrary-length DFT through the power-of-two engine)
+// ---------------------------------------------------------------------------------------
+// chirp[n] = exp(-i*pi*n^2/N); n^2 is reduced mod 2N in integers so the angle is exact
+__device__ __forceinline__ float2 chirp_at(unsigned long long n, unsigned long long N) {
+    const unsigned long long e = (n * n) % (2ULL * N);
+    double s, c;
+    sincospi((double)e / (double)N, &s, &c);
+    return make_float2((float)c, (float)(-s));
+}
+
+// a[n] = x[n]*chirp[n] (n < N, else 0);  cc[m] = chirp[min(m, Lp-m)] for |m| < N (else 0)
+__global__ void __launch_bounds__(256) k_bluestein_prepare(const float2* __restrict__ x, unsigned long long N,
+                                                           unsigned long long Lp, float2* __restrict__ a,
+                                                           float2* __restrict__ cc) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < Lp;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        float2 av = make_float2(0.f, 0.f), cv = make_float2(0.f, 0.f);
+        if (i < N) {
+            const float2 w = chirp_at(i, N);
+            av = cmul(x[i], w);
+            cv = w;
+        } else if (Lp - i < N) {
+            cv = chirp_at(Lp - i, N);
+        }
+        a[i] = av;
+        cc[i] = cv;
+    }
+}
+
+// X[k] = chirp[k] * conv[k]
+__global__ void __launch_bounds__(256) k_bluestein_finish(const float2* __restrict__ conv, unsigned long long N,
+                                                          float2* __restrict__ X) {
+    for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < N;
+         k += (unsigned long long)gridDim.x * blockDim.x)
+        X[k] = cmul(conv[k], chirp_at(k, N));
+}
+
+extern "C" int rmx_bluestein_prepare(const rmx_complex64* x, size_t n, size_t padded_len, rmx_complex64* a,
+                                     rmx_complex64* chirp_circ, void* stream) {
+    if (!x || !a || !chirp_circ) return fail(RMX_ERR_ARG, "null argument to rmx_bluestein_prepare");
+    if (n == 0 || padded_len < 2 * n - 1) return fail(RMX_ERR_ARG, "padded_len must be >= 2n-1");
+    k_bluestein_prepare<<<grid_for((long long)padded_len, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(x), n, padded_len, reinterpret_cast<float2*>(a), reinterpret_cast<float2*>(chirp_circ));
+    LAUNCH_CHECK("bluestein_prepare");
+    return RMX_OK;
+}
+
+extern "C" int rmx_bluestein_finish(const rmx_complex64* conv, size_t n, rmx_complex64* out, void* stream) {
+    if (!conv || !out) return fail(RMX_ERR_ARG, "null argument to rmx_bluestein_finish");
+    if (n == 0) return RMX_OK;
+    k_bluestein_finish<<<grid_for((long long)n, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(conv), n, reinterpret_cast<float2*>(out));
+    LAUNCH_CHECK("bluestein_finish");
+    return RMX_OK;
+}
+
+// out[k] = 20*log10(|x[k]| + 1e-12) for a natural-order complex vector, optional fftshift
+__global__ void __launch_bounds__(256) k_abs_db(const float2* __restrict__ x, size_t n, float* __restrict__ out, int shift) {
+    const size_t half = n / 2;      // np.fft.fftshift moves index k to (k + n//2) % n
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const float2 v = x[k];
+        size_t dst = k;
+        if (shift) { dst = k + half; if (dst >= n) dst -= n; }
+        out[dst] = 20.0f * log10f(hypotf(v.x, v.y) + 1e-12f);
+    }
+}
+
+extern "C" int rmx_abs_db(const rmx_complex64* x, size_t n, float* out_db, int shift, void* stream) {
+    if (!x || !out_db) return fail(RMX_ERR_ARG, "null argument to rmx_abs_db");
+    if (n == 0) return RMX_OK;
+    k_abs_db<<<grid_for((long long)n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(x), n, out_db, shift);
+    LAUNCH_CHECK("abs_db");
+    return RMX_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // layout helpers, dB spectrum
 // ---------------------------------------------------------------------------------------
@@ -564,10 +699,6 @@ __global__ void k_spectrum_db(LayoutDesc d, const float2* __restrict__ in, float
     }
 }
 
-static unsigned grid_for(long long total, int block) {
-    long long g = (total + block - 1) / block;
-    return (unsigned)std::min<long long>(g, 148LL * 16);
-}
 
 extern "C" int rmx_spectrum_natural(const rmx_plan* pl, const rmx_complex64* spectra, rmx_complex64* out,
                                     int n_signals, void* stream) {
@@ -943,6 +1074,49 @@ extern "C" int rmx_signal_energy(const uint8_t* iq, size_t signal_stride_bytes, 
     const unsigned bx = (unsigned)std::max<long long>(1, std::min<long long>((long long)(n_samples / 8 + 255) / 256, 296 / std::max(1, std::min(n_signals, 296)) + 1));
     k_signal_energy<<<dim3(bx, n_signals), 256, 0, st>>>(iq, signal_stride_bytes, n_samples, out);
     LAUNCH_CHECK("signal_energy");
+    return RMX_OK;
+}
+
+// statistics of complex64 samples: double sum of |x|^2 and max |x|^2 (x^2 + y^2 is exact in double,
+// so the final sqrt is the correctly rounded |x| that numpy's hypot-based np.abs returns)
+__global__ void __launch_bounds__(256) k_signal_stats_c64(const float2* __restrict__ x, size_t n, double* __restrict__ sum_out,
+                                                          unsigned long long* __restrict__ max_out) {
+    double sum = 0.0, mx = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float2 v = x[i];
+        sum += (double)(v.x * v.x + v.y * v.y);          // float32 |x|^2 like np.abs(x)**2, accumulated in double
+        mx = fmax(mx, (double)v.x * (double)v.x + (double)v.y * (double)v.y);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(sum_out, sum);
+        atomicMax(max_out, (unsigned long long)__double_as_longlong(mx));   // non-negative doubles order like their bits
+    }
+}
+
+__global__ void k_signal_stats_c64_final(const double* __restrict__ sum_in, const unsigned long long* __restrict__ max_in,
+                                         size_t n, rmx_stats* __restrict__ out) {
+    rmx_stats s;
+    s.mean_power = *sum_in / (double)n;
+    s.peak_amplitude = (float)sqrt(__longlong_as_double((long long)*max_in));
+    s.pad = 0.f;
+    *out = s;
+}
+
+extern "C" int rmx_signal_stats_c64(const rmx_complex64* x, size_t n_samples, rmx_stats* out, void* workspace, void* stream) {
+    if (!x || !out || !workspace) return fail(RMX_ERR_ARG, "null argument to rmx_signal_stats_c64");
+    if (n_samples == 0) return fail(RMX_ERR_ARG, "rmx_signal_stats_c64 needs n_samples > 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* sum = reinterpret_cast<double*>(workspace);
+    unsigned long long* mx = reinterpret_cast<unsigned long long*>(sum + 1);
+    CUDA_TRY(cudaMemsetAsync(workspace, 0, 16, st));
+    k_signal_stats_c64<<<grid_for((long long)n_samples, 256), 256, 0, st>>>(reinterpret_cast<const float2*>(x), n_samples, sum, mx);
+    LAUNCH_CHECK("signal_stats_c64");
+    k_signal_stats_c64_final<<<1, 1, 0, st>>>(sum, mx, n_samples, out);
+    LAUNCH_CHECK("signal_stats_c64_final");
     return RMX_OK;
 }
 

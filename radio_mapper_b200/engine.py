@@ -142,6 +142,18 @@ class Plan:
                           "rmx_fft_forward_cu8")
         return out
 
+    def forward_c64(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """complex64[n_signals, N] (device) -> spectra complex64[n_signals, L] in the plan layout."""
+        _require_cuda(x, torch.complex64, "x")
+        if x.numel() != self.n_signals * self.n_samples:
+            raise ValueError("x has %d samples, plan expects %d x %d" % (x.numel(), self.n_signals, self.n_samples))
+        if out is None:
+            out = torch.empty((self.n_signals, self.fft_len), dtype=torch.complex64, device=self.device)
+        _require_cuda(out, torch.complex64, "out")
+        with torch.cuda.device(self.device):
+            _native.check(_lib.rmx_fft_forward_c64(self._h, _ptr(x), 0, _ptr(out), _stream_ptr()), "rmx_fft_forward_c64")
+        return out
+
     # ---- profiling -----------------------------------------------------------------------
     def profile(self, enable: bool = True):
         _native.check(_lib.rmx_profile_enable(self._h, int(bool(enable))), "rmx_profile_enable")
@@ -191,6 +203,19 @@ class Plan:
         with torch.cuda.device(self.device):
             _native.check(_lib.rmx_xcorr_pairs_peak(self._h, _ptr(spectra), _ptr(pairs), n_pairs, _ptr(out), _ptr(ws),
                                                     ws.numel(), _stream_ptr()), "rmx_xcorr_pairs_peak")
+        return out
+
+    def xcorr_full(self, spectra: torch.Tensor, pairs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Full correlation ifft(X_j conj X_i) per pair, natural order: complex64[P, L]."""
+        _require_cuda(spectra, torch.complex64, "spectra")
+        _require_cuda(pairs, torch.int32, "pairs")
+        n_pairs = pairs.shape[0]
+        if out is None:
+            out = torch.empty((n_pairs, self.fft_len), dtype=torch.complex64, device=self.device)
+        _require_cuda(out, torch.complex64, "out")
+        with torch.cuda.device(self.device):
+            _native.check(_lib.rmx_xcorr_full(self._h, _ptr(spectra), _ptr(pairs), n_pairs, _ptr(out), _stream_ptr()),
+                          "rmx_xcorr_full")
         return out
 
     def welch_psd(self, iq_u8: torch.Tensor, sample_rate: float, segments_in_flight: int = 64) -> torch.Tensor:
@@ -262,6 +287,17 @@ def mean_median(db: torch.Tensor):
     return np.float32(m[0]), np.float32(m[1])
 
 
+def signal_stats_c64(x: torch.Tensor):
+    """(mean |x|^2 as float64, max |x| as float32) of complex64 device samples."""
+    _require_cuda(x, torch.complex64, "x")
+    out = torch.empty(32, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _native.check(_lib.rmx_signal_stats_c64(_ptr(x), x.numel(), _ptr(out), ctypes.c_void_p(out.data_ptr() + 16),
+                                                _stream_ptr()), "rmx_signal_stats_c64")
+    raw = out.cpu().numpy()
+    return float(raw[:8].view(np.float64)[0]), np.float32(raw[8:12].view(np.float32)[0])
+
+
 def signal_stats(iq_u8: torch.Tensor):
     """(mean |x|^2 as float64, max |x| as float32) straight from the cu8 bytes."""
     _require_cuda(iq_u8, torch.uint8, "iq_u8")
@@ -270,3 +306,24 @@ def signal_stats(iq_u8: torch.Tensor):
         _native.check(_lib.rmx_signal_stats(_ptr(iq_u8), iq_u8.numel() // 2, _ptr(out), _stream_ptr()), "rmx_signal_stats")
     raw = out.cpu().numpy()
     return float(raw[:8].view(np.float64)[0]), np.float32(raw[8:12].view(np.float32)[0])
+
+
+def is_pow2(n: int) -> bool:
+    return n > 0 and (n & (n - 1)) == 0
+
+
+def spectrum_db_c64(x: torch.Tensor, shift: bool = False, plans: Optional[dict] = None) -> torch.Tensor:
+    """20*log10(|fft(x)| + 1e-12) of one complex64 device vector, natural (or fftshifted) order.
+    Power-of-two lengths use the tile FFT directly; other lengths go through `bluestein`."""
+    _require_cuda(x, torch.complex64, "x")
+    n = x.numel()
+    if n < 16 or not is_pow2(n):
+        from . import bluestein
+        return bluestein.spectrum_db(x.reshape(-1), shift=shift, plans=plans)
+    key = (1, n, n)
+    plan = plans.get(key) if plans is not None else None
+    if plan is None:
+        plan = Plan(1, n, n, device=x.device)
+        if plans is not None:
+            plans[key] = plan
+    return plan.spectrum_db(plan.forward_c64(x.reshape(1, n)), shift=shift)[0]

@@ -1,0 +1,72 @@
+"""CPU: the C-ABI library loads and exports every symbol include/rmx.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from radio_mapper_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    with open(os.path.join(ROOT, "include", "rmx.h")) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"RMX_API\s+[\w\s\*]+?\b(rmx_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.load()
+    names = _header_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), name
+    assert sorted(_native.SIGNATURES) == names        # the ctypes table covers the header, no more, no less
+    assert lib.rmx_version() == 100
+
+
+def test_header_cites_reference_lines():
+    with open(os.path.join(ROOT, "include", "rmx.h")) as f:
+        text = f.read()
+    for cite in ("buoy_node.py:392-398", "tdoa_processor.py:51", "signal_analyzer.py:92-99", "buoy_node.py:411-415"):
+        assert cite in text
+
+
+def test_bad_arguments_return_negative_status_with_message():
+    lib = _native.load()
+    h = ctypes.c_void_p()
+    assert lib.rmx_plan_create(ctypes.byref(h), 0, 16, 16, 0) == -1
+    assert b"n_signals" in lib.rmx_last_error()
+    assert lib.rmx_plan_create(ctypes.byref(h), 1, 16, 24, 0) == -2          # not a power of two
+    assert b"power of two" in lib.rmx_last_error()
+    assert lib.rmx_plan_create(ctypes.byref(h), 1, 32, 16, 0) == -1          # n_samples > fft_len
+    assert lib.rmx_plan_create(ctypes.byref(h), 1, 4, 8, 0) == -2            # below the minimum length
+    assert lib.rmx_unpack_cu8(None, None, 5, None) == -1
+    assert lib.rmx_unpack_cu8(None, None, 0, None) == 0                      # empty input is a no-op
+    with pytest.raises(_native.RmxError):
+        _native.check(lib.rmx_threshold_peaks(None, 10, 0.0, None, None, 4, None), "rmx_threshold_peaks")
+
+
+def test_single_stage_plan_needs_no_device():
+    """Plans whose transform fits one radix stage own no device tables: creating one, querying its
+    layout and workspace size are pure host calls."""
+    lib = _native.load()
+    h = ctypes.c_void_p()
+    assert lib.rmx_plan_create(ctypes.byref(h), 3, 8, 16, 0) == 0
+    buf = (ctypes.c_int32 * 8)()
+    assert lib.rmx_plan_layout(h, buf, 8) == 1 and buf[0] == 16
+    assert lib.rmx_plan_workspace_bytes(h, 3) >= 3 * 16 * 8
+    assert lib.rmx_plan_set_max_lag(h, 3) == 0
+    assert lib.rmx_plan_destroy(h) == 0
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from radio_mapper_b200 import engine
+    with pytest.raises(RuntimeError):
+        engine.Plan(2, 64)
+    with pytest.raises(ValueError):
+        engine.unpack_cu8(torch.zeros(8, dtype=torch.uint8))                # CPU tensor: no fallback

@@ -1,0 +1,265 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, the golden
+vectors produced by the reference, and size-independent properties at BASELINE sizes.
+
+Tolerances (BASELINE.json north_star): cu8 unpack and integer lags bit-exact; correlation peak
+values 1e-4 relative; sub-sample delays 1e-3 samples.  Spectra: rel-L2 <= 1e-5 (measured ~2e-7);
+dB spectra 1e-3 dB away from deep nulls; identical detected-bin sets away from the threshold.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.fft
+import scipy.signal
+
+import oracle
+from radio_mapper_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+PEAK_RTOL = 1e-4
+FRAC_ATOL = 1e-3
+
+
+def _cuda(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _check_records(got, ref):
+    assert np.array_equal(got["lag"], ref["lag"]), (got["lag"], ref["lag"])
+    assert np.max(np.abs(got["peak"] / ref["peak"] - 1)) <= PEAK_RTOL
+    assert np.max(np.abs(got["frac"] - ref["frac"])) <= FRAC_ATOL
+
+
+# ---- stage 1 -----------------------------------------------------------------------------
+def test_unpack_bit_exact_against_reference_golden(rmx, golden_dir):
+    g = np.load(os.path.join(golden_dir, "unpack.npz"))
+    got = rmx.unpack_cu8(_cuda(g["raw"])).cpu().numpy()
+    assert got.dtype == np.complex64
+    assert np.array_equal(got.view(np.uint32), g["x_file"].view(np.uint32))
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 4099, 1 << 16, (1 << 20) + 5])
+def test_unpack_bit_exact_random(rmx, n):
+    rng = np.random.default_rng(n)
+    raw = rng.integers(0, 256, size=2 * n, dtype=np.uint8)
+    got = rmx.unpack_cu8(_cuda(raw)).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), oracle.unpack_cu8(raw).view(np.uint32))
+    # unaligned view (scalar path)
+    if n > 8:
+        import torch
+        t = _cuda(np.concatenate([[0, 0], raw]).astype(np.uint8))[2:]
+        got2 = rmx.unpack_cu8(t.clone() if False else t.contiguous()).cpu().numpy()
+        assert np.array_equal(got2.view(np.uint32), oracle.unpack_cu8(raw).view(np.uint32))
+
+
+def test_unpack_empty(rmx):
+    import torch
+    out = rmx.unpack_cu8(torch.empty(0, dtype=torch.uint8, device="cuda"))
+    assert out.numel() == 0
+
+
+# ---- stage 2 -----------------------------------------------------------------------------
+@pytest.mark.parametrize("logL", [4, 5, 7, 9, 12, 13, 14, 16, 17, 19, 21, 22, 24])
+def test_forward_fft_vs_scipy(rmx, logL):
+    L = 1 << logL
+    rng = np.random.default_rng(logL)
+    B = 3 if logL <= 20 else 2
+    for N in sorted({L, L // 2, max(1, L // 2 - 3)}):
+        raw = rng.integers(0, 256, size=(B, 2 * N), dtype=np.uint8)
+        plan = rmx.Plan(B, N, L)
+        S = plan.forward(_cuda(raw))
+        nat = plan.spectrum_natural(S).cpu().numpy()
+        x = np.zeros((B, L), np.complex64)
+        for b in range(B):
+            x[b, :N] = oracle.unpack_cu8(raw[b])
+        ref = scipy.fft.fft(x.astype(np.complex128), axis=1)
+        err = np.linalg.norm(nat - ref) / np.linalg.norm(ref)
+        assert err < 1e-6, (logL, N, plan.pass_lengths, err)
+        # the documented layout: position p holds bin layout_freq_index()[p]
+        lay = S.cpu().numpy()
+        assert np.array_equal(lay, nat[:, plan.layout_freq_index()])
+        # complex64 entry point gives the same spectrum
+        S2 = plan.forward_c64(_cuda(x[:, :N].copy()))
+        assert np.linalg.norm(S2.cpu().numpy() - lay) / np.linalg.norm(lay) < 1e-6
+        # and matches the reference's own complex64 scipy.fft.fft within fp32 rounding
+        ref32 = oracle.forward_fft(x[0])
+        assert np.linalg.norm(nat[0] - ref32) / np.linalg.norm(ref32) < 2e-6
+
+
+def test_strided_input_rows(rmx):
+    """One window cut out of a [buoy, stream] buffer (row stride > 2N)."""
+    rng = np.random.default_rng(5)
+    B, W, N = 3, 4, 4096
+    raw = rng.integers(0, 256, size=(B, W, 2 * N), dtype=np.uint8)
+    dev = _cuda(raw)
+    plan = rmx.Plan(B, N)
+    a = plan.forward(dev[:, 2, :]).cpu().numpy()
+    b = plan.forward(_cuda(raw[:, 2, :].copy())).cpu().numpy()
+    assert np.array_equal(a, b)
+
+
+# ---- stages 3+4 ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n_samples,n_buoys", [(8, 3), (100, 3), (1000, 4), (2048, 4), (4096, 4), (5000, 3),
+                                               (1 << 14, 5), (1 << 16, 4), (100000, 3), (1 << 18, 3), (1 << 20, 3)])
+def test_xcorr_peak_parity(rmx, n_samples, n_buoys):
+    iq, delays, _ = synth.delayed_buoys(100 + n_samples, n_buoys, n_samples, max_delay=min(342, max(1, n_samples // 4)))
+    ref = oracle.xcorr_pairs_peak(iq)
+    plan = rmx.Plan(n_buoys, n_samples)
+    S = plan.forward(_cuda(iq))
+    got = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, _cuda(rmx.pair_table(n_buoys))))
+    _check_records(got, ref)
+    if n_samples >= 1000:          # and both equal the ground truth the generator used
+        assert list(got["lag"]) == [delays[j] - delays[i] for i, j in oracle.pair_list(n_buoys)]
+
+
+def test_xcorr_chunked_workspace_and_pair_subsets(rmx):
+    iq, delays, _ = synth.delayed_buoys(77, 6, 1 << 15)
+    ref = oracle.xcorr_pairs_peak(iq)
+    plan = rmx.Plan(6, 1 << 15)
+    S = plan.forward(_cuda(iq))
+    pairs = rmx.pair_table(6)
+    a = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, _cuda(pairs), max_pairs_in_flight=4))
+    _check_records(a, ref)
+    sel = np.array([14, 3, 3, 0], dtype=np.int64)            # arbitrary order, duplicates allowed
+    b = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, _cuda(pairs[sel])))
+    _check_records(b, ref[sel])
+    # reversed pair (j, i) negates the lag
+    c = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, _cuda(pairs[:, ::-1].copy())))
+    assert np.array_equal(c["lag"], -ref["lag"])
+    # empty pair list
+    import torch
+    assert plan.xcorr_pairs_peak(S, torch.empty((0, 2), dtype=torch.int32, device="cuda")).shape[0] == 0
+
+
+@pytest.mark.parametrize("max_lag", [0, 5, 342, 5000])
+def test_xcorr_max_lag_window(rmx, max_lag):
+    iq, delays, _ = synth.delayed_buoys(31, 4, 1 << 14, max_delay=300)
+    ref = oracle.xcorr_pairs_peak(iq, max_lag=max_lag)
+    plan = rmx.Plan(4, 1 << 14)
+    plan.set_max_lag(max_lag)
+    S = plan.forward(_cuda(iq))
+    got = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, _cuda(rmx.pair_table(4))))
+    assert np.array_equal(got["lag"], ref["lag"])
+    assert np.max(np.abs(got["peak"] / ref["peak"] - 1)) <= PEAK_RTOL
+    assert np.max(np.abs(got["frac"] - ref["frac"])) <= FRAC_ATOL
+    plan.set_max_lag(None)
+    full = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, _cuda(rmx.pair_table(4))))
+    assert np.array_equal(full["lag"], oracle.xcorr_pairs_peak(iq)["lag"])
+
+
+def test_xcorr_edge_inputs(rmx):
+    """Saturated / constant inputs and peaks on the edge of the lag range."""
+    n = 4096
+    rng = np.random.default_rng(9)
+    base = rng.integers(0, 256, size=2 * n, dtype=np.uint8)
+    iq = np.stack([base,
+                   np.roll(base, 2 * (n - 1)),                  # circular shift: peak near the range edge
+                   np.full(2 * n, 255, np.uint8),               # saturated constant
+                   np.where(rng.random(2 * n) < 0.5, 0, 255).astype(np.uint8)])   # full-scale square noise
+    ref = oracle.xcorr_pairs_peak(iq)
+    plan = rmx.Plan(4, n)
+    got = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(plan.forward(_cuda(iq)), _cuda(rmx.pair_table(4))))
+    truth = oracle.xcorr_pairs_peak(iq, dtype=np.complex128)
+    for k in range(len(ref)):
+        # where float32 and float64 oracles disagree the arg-max is numerically ambiguous
+        if ref["lag"][k] == truth["lag"][k]:
+            assert got["lag"][k] == ref["lag"][k], k
+            assert abs(got["peak"][k] / ref["peak"][k] - 1) <= PEAK_RTOL
+    # identical signals: peak exactly at lag 0 with the signal energy as the peak value
+    same = np.stack([base, base])
+    plan2 = rmx.Plan(2, n)
+    r = rmx.peaks_to_numpy(plan2.xcorr_pairs_peak(plan2.forward(_cuda(same)), _cuda(rmx.pair_table(2))))
+    energy = float(np.sum(np.abs(oracle.unpack_cu8(base).astype(np.complex128)) ** 2))
+    assert r["lag"][0] == 0 and abs(r["peak"][0] / energy - 1) < 1e-5 and abs(r["frac"][0]) < 1e-3
+
+
+def test_xcorr_full_output_matches_scipy(rmx):
+    iq, _, _ = synth.delayed_buoys(5, 3, 3000)
+    plan = rmx.Plan(3, 3000)
+    S = plan.forward(_cuda(iq))
+    c = plan.xcorr_full(S, _cuda(rmx.pair_table(3))).cpu().numpy()
+    L = plan.fft_len
+    for p, (i, j) in enumerate(oracle.pair_list(3)):
+        ref, lags = oracle.xcorr_full(oracle.unpack_cu8(iq[i]), oracle.unpack_cu8(iq[j]), dtype=np.complex128)
+        got = c[p][lags % L]
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 2e-6
+
+
+def test_fractional_delay_accuracy(rmx):
+    """Sub-sample delays: GPU frac == oracle frac within 1e-3, and both track the true delay."""
+    fr = [0.0, 0.3, -0.2, 0.12]
+    iq, d, f = synth.delayed_buoys(11, 4, 1 << 16, snr_db=20, frac_delays=fr)
+    ref = oracle.xcorr_pairs_peak(iq)
+    plan = rmx.Plan(4, 1 << 16)
+    got = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(plan.forward(_cuda(iq)), _cuda(rmx.pair_table(4))))
+    _check_records(got, ref)
+    true = np.array([(d[j] + f[j]) - (d[i] + f[i]) for i, j in oracle.pair_list(4)])
+    assert np.max(np.abs(got["lag"] + got["frac"] - true)) < 0.1
+
+
+# ---- BASELINE-sized properties ----------------------------------------------------------------
+def _delays_ok(rmx, n_buoys, log_samples, seed, n_windows=1):
+    import torch
+    iq, delays = synth.delayed_buoys_torch(seed, n_buoys, n_windows, 1 << log_samples, torch.device("cuda"))
+    plan = rmx.Plan(n_buoys, 1 << log_samples)
+    pairs_h = rmx.pair_table(n_buoys)
+    pairs = _cuda(pairs_h)
+    for w in range(n_windows):
+        S = plan.forward(iq[:, w, :])
+        got = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, pairs))
+        want = delays[w, pairs_h[:, 1]] - delays[w, pairs_h[:, 0]]
+        assert np.array_equal(got["lag"], want)
+        assert np.all(np.abs(got["frac"]) < 0.2) and np.all(got["peak"] > 0)
+    return plan
+
+
+def test_cfg3_size_known_delays(rmx):
+    """16 buoys / 120 pairs / N = 2^22 (L = 2^23): every lag equals the generator's delay."""
+    plan = _delays_ok(rmx, 16, 22, 303)
+    assert plan.fft_len == 1 << 23
+
+
+def test_cfg4_size_known_delays(rmx):
+    """64 buoys / 2016 pairs / N = 2^20."""
+    _delays_ok(rmx, 64, 20, 404)
+
+
+def test_cfg5_size_known_delays(rmx):
+    """N = 2^26 (L = 2^27, three passes): 3 buoys of the 8 to bound memory and time."""
+    plan = _delays_ok(rmx, 3, 26, 505)
+    assert len(plan.pass_lengths) == 3
+
+
+def test_cfg1_exact_reference_case(rmx):
+    """3 buoys, 2 048 000 samples (not a power of two), 3 pairs — compared with the oracle."""
+    iq, delays, _ = synth.delayed_buoys(1000, 3, 2_048_000)
+    ref = oracle.xcorr_pairs_peak(iq)
+    plan = rmx.Plan(3, 2_048_000)
+    assert plan.fft_len == 1 << 22
+    got = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(plan.forward(_cuda(iq)), _cuda(rmx.pair_table(3))))
+    _check_records(got, ref)
+    assert list(got["lag"]) == [delays[j] - delays[i] for i, j in oracle.pair_list(3)]
+
+
+def test_linearity_and_shift_properties(rmx):
+    """Size-independent properties at 2^20: the correlation of a signal with its own circular
+    shift peaks at the shift; swapping the pair negates the lag; scaling the input scales |c|."""
+    import torch
+    n = 1 << 20
+    rng = np.random.default_rng(1)
+    a = rng.integers(96, 160, size=2 * n, dtype=np.uint8)
+    shift = 12345
+    b = np.roll(a, 2 * shift)
+    iq = np.stack([a, b])
+    plan = rmx.Plan(2, n)
+    S = plan.forward(_cuda(iq))
+    r = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, _cuda(np.array([[0, 1], [1, 0]], dtype=np.int32))))
+    assert r["lag"][0] == shift and r["lag"][1] == -shift
+    assert abs(r["peak"][0] / r["peak"][1] - 1) < 1e-5
+    # Parseval on the spectra: sum|X|^2 == L * sum|x|^2
+    x = oracle.unpack_cu8(a).astype(np.complex128)
+    e_spec = float((S[0].abs().double() ** 2).sum().item())
+    assert abs(e_spec / (plan.fft_len * np.sum(np.abs(x) ** 2)) - 1) < 1e-5
