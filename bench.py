@@ -233,6 +233,34 @@ def run_b200(args, wl):
         elapsed_ms = float(t.item())
     value = P * N * W * world * args.steps / (elapsed_ms * 1e-3)
 
+    # ---- one-pass windowed search (|lag| <= 2*342 samples: every lag two buoys within a 50 km
+    #      radius of the source can produce, reference config.yaml:145) — reported beside the
+    #      full-range headline, never instead of it ------------------------------------------
+    win_lag = 2 * 342
+    plan.set_max_lag(win_lag)
+    for _ in range(3):
+        rec_w, _ = step()
+    torch.cuda.synchronize()
+    got_w = rec_w[:W].cpu().numpy()[..., 0] if world == 1 else rec_w[rank * W:(rank + 1) * W].cpu().numpy()[..., 0]
+    windowed_ok = bool(np.array_equal(got_w, want))
+    if world > 1:
+        dist.barrier()
+    plan.profile(True)
+    evw0, evw1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evw0.record()
+    for _ in range(args.steps):
+        step()
+    evw1.record()
+    torch.cuda.synchronize()
+    win_ms = evw0.elapsed_time(evw1)
+    prof_w = plan.profile_collect()
+    plan.profile(False)
+    plan.set_max_lag(None)
+    if world > 1:
+        t = torch.tensor([win_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        win_ms = float(t.item())
+
     # ---- end to end through the public API: pinned host cu8 -> TDoAMeasurement list ----------
     iq_host = torch.empty(iq_dev.shape, dtype=torch.uint8, pin_memory=True)
     iq_host.copy_(iq_dev)
@@ -278,6 +306,16 @@ def run_b200(args, wl):
         "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items())},
     }
 
+    win_pair_ms = sum(v[1] for k, v in prof_w.items() if k.startswith(("contig_inv", "finalize")))
+    windowed = {
+        "max_lag": win_lag, "lags_match_full_search": windowed_ok,
+        "value": P * N * W * world * args.steps / (win_ms * 1e-3), "unit": UNIT, "ms_per_step": win_ms / args.steps,
+        "pair_stage": {"achieved": pair_b * n_calls / (win_pair_ms * 1e-3) / 1e9 if win_pair_ms > 0 else 0.0, "unit": "GB/s",
+                       "frac": (pair_b * n_calls / (win_pair_ms * 1e-3) / 1e9 / peak) if win_pair_ms > 0 else 0.0,
+                       "note": "algorithmic bytes / time; spectra are re-read from L2, so this can exceed what HBM alone delivers"},
+        "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof_w.items())},
+    }
+
     # ---- CPU baseline: the oracle on a bounded sample, this box's host cores ---------------------
     b = 4 if N <= (1 << 22) else 2
     sample_iq = iq_host[:b, 0, :].numpy()
@@ -305,6 +343,7 @@ def run_b200(args, wl):
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "windowed_search": windowed,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -82,6 +82,12 @@ RMX_API size_t rmx_plan_workspace_bytes(const rmx_plan* plan, int n_pairs);
  * -(n_samples-1) .. n_samples-1 of scipy.signal.correlate(mode='full') */
 RMX_API int rmx_plan_set_max_lag(rmx_plan* plan, long long max_lag);
 
+/* With a lag window much narrower than a row of the innermost pass (max_lag < 2048) the search
+ * runs as ONE pass over the spectra (row iFFT + twiddled accumulation of the kept lags, no
+ * correlation workspace).  force_full != 0 disables that path (the full inverse transform with a
+ * masked arg-max is used instead); results are identical up to float rounding. */
+RMX_API int rmx_plan_set_search_mode(rmx_plan* plan, int force_full);
+
 /* Stages 1+2 — fused unpack + zero-pad + batched forward FFT of all signals.
  * iq: signal s starts at iq + s*signal_stride_bytes (0 = densely packed, 2*n_samples) and holds
  * 2*n_samples bytes; spectra: complex64[n_signals][fft_len] (plan layout).

@@ -22,6 +22,7 @@ SIGNATURES = {
     "rmx_plan_layout": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_int32), c_int]),
     "rmx_plan_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "rmx_plan_set_max_lag": (c_int, [c_void_p, c_longlong]),
+    "rmx_plan_set_search_mode": (c_int, [c_void_p, c_int]),
     "rmx_fft_forward_cu8": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "rmx_fft_forward_c64": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "rmx_signal_stats_c64": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),

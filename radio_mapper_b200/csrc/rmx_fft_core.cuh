@@ -263,9 +263,11 @@ __device__ __forceinline__ float2 unit_root(uint32_t p, int logm, bool inverse) 
 // log2(E), so the worst-case error stays at a few ulp.
 template <int E>
 __device__ __forceinline__ void row_twiddles(float2 (&tw)[E], uint32_t j, uint32_t i0, uint32_t step_rows,
-                                             int logm, bool inverse) {
+                                             int logm, bool inverse, float scale) {
     const uint32_t mask = (logm >= 32) ? 0xffffffffu : ((1u << logm) - 1u);
     tw[0] = unit_root((j * i0) & mask, logm, inverse);
+    tw[0].x *= scale;                 // a power of two: exact, and it propagates through the product tree
+    tw[0].y *= scale;
     float2 pw = make_float2(1.f, 0.f);
     static_for<0, ilog2(E)>([&](auto Z_) {
         constexpr int z = decltype(Z_)::value;

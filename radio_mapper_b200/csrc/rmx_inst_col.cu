@@ -6,7 +6,7 @@ namespace rmx {
 template <int LOGN, int LOGE, int MODE>
 static KernelEntry col_entry() {
     using GEO = TileGeom<LOGN, LOGE, true>;
-    return KernelEntry{(PassKernel)k_col<LOGN, LOGE, MODE>, GEO::SMEM_BYTES, GEO::LOGG};
+    return KernelEntry{(PassKernel)k_col<LOGN, LOGE, MODE>, GEO::SMEM_BYTES > size_t(GEO::TILE) * 2 ? GEO::SMEM_BYTES : size_t(GEO::TILE) * 2, GEO::LOGG};
 }
 
 template <int LOGE, int MODE>

@@ -6,7 +6,7 @@ namespace rmx {
 template <int LOGN, int MODE>
 static KernelEntry col32_entry() {
     using GEO = TileGeom<LOGN, 5, true>;
-    return KernelEntry{(PassKernel)k_col<LOGN, 5, MODE>, GEO::SMEM_BYTES, GEO::LOGG};
+    return KernelEntry{(PassKernel)k_col<LOGN, 5, MODE>, GEO::SMEM_BYTES > size_t(GEO::TILE) * 2 ? GEO::SMEM_BYTES : size_t(GEO::TILE) * 2, GEO::LOGG};
 }
 
 template <int MODE>

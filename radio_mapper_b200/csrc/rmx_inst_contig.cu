@@ -35,6 +35,9 @@ KernelEntry get_contig_kernel(int logn, int loge, int mode) {
         case C_FWD_CU8: return contig_by_logn<4, C_FWD_CU8>(logn);
         case C_INV_PAIR: return contig_by_logn<4, C_INV_PAIR>(logn);
         case C_FWD_PSD: return contig_by_logn<4, C_FWD_PSD>(logn);
+        case C_INV_PAIR_WIN2: return logn == 12 ? contig_entry<12, 4, C_INV_PAIR_WIN2>() : KernelEntry{nullptr, 0, 0};
+        case C_INV_PAIR_WIN4: return logn == 12 ? contig_entry<12, 4, C_INV_PAIR_WIN4>() : KernelEntry{nullptr, 0, 0};
+        case C_INV_PAIR_WIN8: return logn == 12 ? contig_entry<12, 4, C_INV_PAIR_WIN8>() : KernelEntry{nullptr, 0, 0};
         default: return KernelEntry{nullptr, 0, 0};
     }
 }

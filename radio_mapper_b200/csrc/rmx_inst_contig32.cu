@@ -16,6 +16,9 @@ KernelEntry get_contig_kernel32(int logn, int mode) {
         case C_FWD_CU8: return contig32_entry<C_FWD_CU8>();
         case C_INV_PAIR: return contig32_entry<C_INV_PAIR>();
         case C_FWD_PSD: return contig32_entry<C_FWD_PSD>();
+        case C_INV_PAIR_WIN2: return contig32_entry<C_INV_PAIR_WIN2>();
+        case C_INV_PAIR_WIN4: return contig32_entry<C_INV_PAIR_WIN4>();
+        case C_INV_PAIR_WIN8: return contig32_entry<C_INV_PAIR_WIN8>();
         default: return KernelEntry{nullptr, 0, 0};
     }
 }

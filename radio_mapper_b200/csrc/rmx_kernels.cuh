@@ -43,11 +43,32 @@ struct PassParams {
     int logS;                 // log2 of the column stride (column kernels)
     int lag_pos_max;          // arg-max searches lags in [-lag_neg_max, lag_pos_max]
     int lag_neg_max;
-    int items_per_cta;        // PSD mode: signals accumulated by one CTA
+    int items_per_cta;        // PSD mode: signals accumulated by one CTA; windowed mode: rows per CTA
     float scale;              // scale folded into the pair product (1/L)
+    // windowed lag search (C_INV_PAIR_WIN*): per-(pair, row chunk) partial sums of the kept lags
+    float2* win_partials;     // [pair][chunk][2*WU*NT]
+    int win_lag_max;          // keep |lag| <= win_lag_max  (< WU*NT)
+    int row_npass;            // number of outer (column) passes whose digits make up a row index
+    int row_logn[kMaxStages]; // their lengths (log2), outermost first
 };
 
-enum ContigMode { C_FWD = 0, C_FWD_CU8 = 1, C_INV_PAIR = 2, C_FWD_PSD = 3 };
+enum ContigMode { C_FWD = 0, C_FWD_CU8 = 1, C_INV_PAIR = 2, C_FWD_PSD = 3, C_INV_PAIR_WIN2 = 4, C_INV_PAIR_WIN4 = 5, C_INV_PAIR_WIN8 = 6 };
+__host__ __device__ constexpr int window_wu(int mode) { return mode == C_INV_PAIR_WIN2 ? 2 : mode == C_INV_PAIR_WIN4 ? 4 : mode == C_INV_PAIR_WIN8 ? 8 : 0; }
+
+// frequency offset phi(rho) of row rho of the digit-transposed layout: row rho = (k_0*n_1 + k_1)*...
+// holds the bins  phi + (n_0*n_1*...)*k_c  with  phi = k_0 + n_0*(k_1 + n_1*(...)).
+__device__ __forceinline__ uint32_t row_frequency(const PassParams& p, uint32_t rho) {
+    uint32_t phi = 0;
+    int shift = 0;
+    for (int t = 0; t < p.row_npass; ++t) shift += p.row_logn[t];
+    int weight = 0;
+    for (int t = 0; t < p.row_npass; ++t) {
+        shift -= p.row_logn[t];
+        phi |= ((rho >> shift) & ((1u << p.row_logn[t]) - 1u)) << weight;
+        weight += p.row_logn[t];
+    }
+    return phi;
+}
 enum ColMode { K_FWD_CU8 = 0, K_FWD = 1, K_INV = 2, K_INV_ARGMAX = 3 };
 
 __device__ __forceinline__ float2 load_cu8_sample(const uint8_t* base, long long idx) {
@@ -97,7 +118,7 @@ template <int LOGN, int LOGE, int MODE>
 __global__ void __launch_bounds__(kThreads) k_contig(const PassParams p) {
     using GEO = TileGeom<LOGN, LOGE, false>;
     constexpr int E = GEO::E, NT = GEO::NT, G = GEO::G;
-    constexpr bool INV = (MODE == C_INV_PAIR);
+    constexpr bool INV = (MODE == C_INV_PAIR || window_wu(MODE) > 0);
     extern __shared__ float2 smem[];
 
     int g, i0;
@@ -105,7 +126,72 @@ __global__ void __launch_bounds__(kThreads) k_contig(const PassParams p) {
     const int log_rows = p.logL - LOGN;               // rows per item (log2)
     float2 r[E];
 
-    if constexpr (MODE == C_FWD_PSD) {
+    if constexpr (window_wu(MODE) > 0) {
+        // Windowed lag search in ONE pass over the spectra.  For |lag| <= win_lag_max only the first
+        // and last WU*NT outputs of every row iFFT matter:
+        //     c[lag] = sum_rows  w_L^{+phi(row)*lag} * ifft_row(X_j conj X_i)[lag mod n]
+        // Each CTA owns a chunk of consecutive rows of one pair, keeps the 2*WU kept outputs per
+        // thread in registers across rows, and writes one partial vector per chunk; no correlation
+        // workspace is written.  Tiles are pair-fastest so spectrum rows are shared through L2.
+        static_assert(GEO::G == 1, "windowed mode needs one row per tile");
+        constexpr int WU = window_wu(MODE);
+        static_assert(2 * WU <= E, "window wider than the row");
+        const unsigned pair_idx = blockIdx.x % (unsigned)p.n_items;
+        const unsigned chunk = blockIdx.x / (unsigned)p.n_items;
+        const int2 pr = p.pairs[pair_idx];
+        const float2* __restrict__ xi = p.spectra + ((long long)pr.x << p.logL);
+        const float2* __restrict__ xj = p.spectra + ((long long)pr.y << p.logL);
+        float2 acc[2 * WU];
+#pragma unroll
+        for (int a = 0; a < 2 * WU; ++a) acc[a] = make_float2(0.f, 0.f);
+        const uint32_t lmask = (1u << p.logL) - 1u;
+        const unsigned row0 = chunk * (unsigned)p.items_per_cta;
+        for (int rr = 0; rr < p.items_per_cta; ++rr) {
+            const unsigned row = row0 + rr;
+            const long long off = ((long long)row << LOGN) + i0;
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+                const float2 a = __ldg(xi + off + u * NT), b = __ldg(xj + off + u * NT);
+                r[u] = cmul_conj(b, a);
+            }
+            fft_tile<GEO, true>(r, smem, g, i0, p.tabs);
+            // twiddle of (row, lag): w_L^{+phi*lag} with lag = a*NT + i0  ->  A * B^a,
+            // A = w^{phi*i0} (per thread), B = w^{phi*NT} (per row); exact roots, short product chains
+            const uint32_t phi = row_frequency(p, row);
+            const float2 A = unit_root((phi * (uint32_t)i0) & lmask, p.logL, true);
+            const float2 B = unit_root((phi * (uint32_t)NT) & lmask, p.logL, true);
+            float2 t = A;
+#pragma unroll
+            for (int a = 0; a < WU; ++a) {                    // lags  a*NT + i0  >= 0   (outputs u = a)
+                if (a * NT <= p.win_lag_max) {                // warp-uniform
+                    if (a * NT + i0 <= p.win_lag_max) {
+                        const float2 v = cmul(r[a], t);
+                        acc[a].x += v.x;
+                        acc[a].y += v.y;
+                    }
+                    t = cmul(t, B);
+                }
+            }
+            t = A;
+#pragma unroll
+            for (int a = 1; a <= WU; ++a) {                   // lags  i0 - a*NT  < 0   (outputs u = E - a)
+                if ((a - 1) * NT < p.win_lag_max) {           // warp-uniform
+                    t = cmul_conj(t, B);
+                    if (i0 - a * NT >= -p.win_lag_max) {
+                        const float2 v = cmul(r[E - a], t);
+                        acc[2 * WU - a].x += v.x;
+                        acc[2 * WU - a].y += v.y;
+                    }
+                }
+            }
+            __syncthreads();                                  // exchange buffer is reused by the next row
+        }
+        const unsigned n_chunks = gridDim.x / (unsigned)p.n_items;
+        float2* __restrict__ out = p.win_partials + ((long long)pair_idx * n_chunks + chunk) * (2 * WU * NT);
+#pragma unroll
+        for (int a = 0; a < 2 * WU; ++a) out[a * NT + i0] = acc[a];
+        return;
+    } else if constexpr (MODE == C_FWD_PSD) {
         // Welch: accumulate |X|^2 of the same rows over items_per_cta consecutive signals.
         // grid = (tiles_per_signal, signal chunks)
         float acc[E];
@@ -163,8 +249,7 @@ __global__ void __launch_bounds__(kThreads) k_contig(const PassParams p) {
             for (int u = 0; u < E; ++u) {
                 if (active) {
                     const float2 a = __ldg(xi + i0 + u * NT), b = __ldg(xj + i0 + u * NT);
-                    const float2 c = cmul_conj(b, a);              // X_j * conj(X_i)
-                    r[u] = make_float2(c.x * p.scale, c.y * p.scale);
+                    r[u] = cmul_conj(b, a);                        // X_j * conj(X_i)
                 } else {
                     r[u] = make_float2(0.f, 0.f);
                 }
@@ -173,6 +258,14 @@ __global__ void __launch_bounds__(kThreads) k_contig(const PassParams p) {
 
         fft_tile<GEO, INV>(r, smem, g, i0, p.tabs);
 
+        if constexpr (MODE == C_INV_PAIR) {
+            // single-pass plans apply the 1/L here; multi-pass plans fold it into the twiddles of
+            // the outermost column pass (p.scale == 1 for this launch)
+            if (p.scale != 1.0f) {
+#pragma unroll
+                for (int u = 0; u < E; ++u) { r[u].x *= p.scale; r[u].y *= p.scale; }
+            }
+        }
         if (active) {
             float2* __restrict__ out = p.dst + item * p.src_item_stride + (row << LOGN);
 #pragma unroll
@@ -208,25 +301,65 @@ __global__ void __launch_bounds__(kThreads) k_col(const PassParams p) {
     float2 r[E];
     if constexpr (MODE == K_FWD_CU8) {
         const uint8_t* __restrict__ in = p.cu8 + item * p.cu8_stride;
+        const long long tile0 = base - g;                   // sample index of (row 0, column 0) of this tile
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)p.cu8_stride) & 15) == 0;
+        if (vec_ok) {
+            // Stage the tile's raw bytes in shared memory with 128-bit loads: every row of the tile is
+            // 2*G contiguous bytes (G >= 8), i.e. whole 16-byte chunks; rows past the valid samples
+            // (zero padding) are never touched.
+            constexpr int CPR = (2 * G) / 16;               // 16-byte chunks per row
+            constexpr int CHUNKS = GEO::N * CPR;
+            uint4* sb4 = reinterpret_cast<uint4*>(smem);
 #pragma unroll
-        for (int u = 0; u < E; ++u) {
-            const long long sidx = base + ((long long)(i0 + u * NT) << logS);
-            float2 v = make_float2(0.f, 0.f);
-            if (sidx < p.n_samples) {
-                v = load_cu8_sample(in, sidx);
-                if (p.window != nullptr) { const float w = __ldg(p.window + sidx); v.x *= w; v.y *= w; }
+            for (int c = threadIdx.x; c < CHUNKS; c += kThreads) {
+                const int row = c / CPR, part = c % CPR;
+                const long long sidx = tile0 + ((long long)row << logS) + part * 8;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (sidx + 8 <= p.n_samples) {
+                    v = __ldg(reinterpret_cast<const uint4*>(in + 2 * sidx));
+                } else if (sidx < p.n_samples) {              // ragged tail of the last valid row
+                    unsigned w[4] = {0u, 0u, 0u, 0u};
+                    for (int b = 0; b < 16 && sidx * 2 + b < 2 * p.n_samples; ++b) w[b >> 2] |= (unsigned)in[2 * sidx + b] << (8 * (b & 3));
+                    v = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                sb4[c] = v;
             }
-            r[u] = v;
+            __syncthreads();
+            const uchar2* sb2 = reinterpret_cast<const uchar2*>(smem);
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+                const int row = i0 + u * NT;
+                const long long sidx = base + ((long long)row << logS);
+                const uchar2 b = sb2[row * G + g];
+                float2 v = make_float2(0.f, 0.f);
+                if (sidx < p.n_samples) v = make_float2((float)b.x - 127.5f, (float)b.y - 127.5f);
+                r[u] = v;
+            }
+            __syncthreads();                                 // the buffer becomes the exchange area
+        } else {
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+                const long long sidx = base + ((long long)(i0 + u * NT) << logS);
+                r[u] = sidx < p.n_samples ? load_cu8_sample(in, sidx) : make_float2(0.f, 0.f);
+            }
+        }
+        if (p.window != nullptr) {
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+                const long long sidx = base + ((long long)(i0 + u * NT) << logS);
+                if (sidx < p.n_samples) { const float w = __ldg(p.window + sidx); r[u].x *= w; r[u].y *= w; }
+            }
         }
     } else {
-        const float2* __restrict__ in = p.src + item * p.src_item_stride + base;
+        const float2* __restrict__ in = p.src + item * p.src_item_stride + base + ((long long)i0 << logS);
+        const long long rstride = (long long)NT << logS;
 #pragma unroll
-        for (int u = 0; u < E; ++u) r[u] = in[(long long)(i0 + u * NT) << logS];
+        for (int u = 0; u < E; ++u) { r[u] = *in; in += rstride; }
     }
 
     if constexpr (INV) {
         float2 tw[E];
-        row_twiddles<E>(tw, j, (uint32_t)i0, (uint32_t)NT, logM, true);
+        row_twiddles<E>(tw, j, (uint32_t)i0, (uint32_t)NT, logM, true, p.scale);
 #pragma unroll
         for (int u = 0; u < E; ++u) r[u] = cmul(r[u], tw[u]);
     }
@@ -235,7 +368,7 @@ __global__ void __launch_bounds__(kThreads) k_col(const PassParams p) {
 
     if constexpr (!INV) {
         float2 tw[E];
-        row_twiddles<E>(tw, j, (uint32_t)i0, (uint32_t)NT, logM, false);
+        row_twiddles<E>(tw, j, (uint32_t)i0, (uint32_t)NT, logM, false, 1.0f);
 #pragma unroll
         for (int u = 0; u < E; ++u) r[u] = cmul(r[u], tw[u]);
     }
@@ -250,11 +383,24 @@ __global__ void __launch_bounds__(kThreads) k_col(const PassParams p) {
         const uint32_t rstep = (uint32_t)NT << logS;
         float v[E];
         float bv = -1.f;
+        // does any lag of this thread's column fall outside the searched range?  The column holds
+        // m = j + row*s for every row; the excluded lags are the ranks in (span, L).
+        const uint32_t col_rank0 = (j + (uint32_t)p.lag_neg_max) & lmask;          // rank of row 0
+        const uint32_t excl = lmask - span;                                          // number of excluded ranks
+        // first excluded rank congruent to col_rank0 modulo s, if there is one
+        const uint32_t smask = (1u << logS) - 1u;
+        const uint32_t first_excl = span + 1u + ((col_rank0 - (span + 1u)) & smask);
+        const bool all_valid = excl == 0u || first_excl > lmask || first_excl < span + 1u;
+        if (all_valid) {
 #pragma unroll
-        for (int u = 0; u < E; ++u) {
-            const uint32_t rank = (rank0 + (uint32_t)u * rstep) & lmask;
-            v[u] = rank <= span ? cnorm2(r[u]) : -1.f;
-            bv = fmaxf(bv, v[u]);
+            for (int u = 0; u < E; ++u) { v[u] = cnorm2(r[u]); bv = fmaxf(bv, v[u]); }
+        } else {
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+                const uint32_t rank = (rank0 + (uint32_t)u * rstep) & lmask;
+                v[u] = rank <= span ? cnorm2(r[u]) : -1.f;
+                bv = fmaxf(bv, v[u]);
+            }
         }
         if constexpr (GEO::NSTAGES > 1) __syncthreads();
         uint32_t brank;
@@ -272,9 +418,10 @@ __global__ void __launch_bounds__(kThreads) k_col(const PassParams p) {
             p.partials[(item << log_tpb) + jt] = out;
         }
     } else {
-        float2* __restrict__ out = p.dst + item * p.src_item_stride + base;
+        float2* __restrict__ out = p.dst + item * p.src_item_stride + base + ((long long)i0 << logS);
+        const long long rstride = (long long)NT << logS;
 #pragma unroll
-        for (int u = 0; u < E; ++u) out[(long long)(i0 + u * NT) << logS] = r[u];
+        for (int u = 0; u < E; ++u) { *out = r[u]; out += rstride; }
     }
 }
 

@@ -68,6 +68,7 @@ struct rmx_plan {
     float* d_hann = nullptr;
     double hann_sumsq = 0.0;
     long long lag_pos_max = 0, lag_neg_max = 0;
+    bool force_full_search = false;   // true: never take the one-pass windowed path
 };
 
 static int build_stage_tables(rmx_plan* pl, int logn, int loge, StageTables* out) {
@@ -202,10 +203,49 @@ static int tiles_per_item_pass0(const rmx_plan* pl) {
     return 1 << (pl->logs[0] - logG);
 }
 
+// One-pass windowed search: usable when the plan has >= 2 passes, the contiguous pass transforms
+// one row per tile, and the lag window fits the first/last WU*NT outputs of a row.
+struct WindowMode {
+    int mode = -1;        // C_INV_PAIR_WIN2 / C_INV_PAIR_WIN8, or -1
+    int slots = 0;        // 2*WU*NT complex partial sums per (pair, chunk)
+    int rows_per_cta = 0;
+    int n_chunks = 0;
+};
+
+static WindowMode window_mode(const rmx_plan* pl) {
+    WindowMode w;
+    if (pl->force_full_search || pl->n_passes < 2 || pl->lag_pos_max != pl->lag_neg_max) return w;
+    const int last = pl->n_passes - 1;
+    if (pl->logn[last] != kLogThreads + pl->loge[last]) return w;
+    const int nt = 1 << kLogThreads;                     // threads per row == rows-step NT
+    const long long m = pl->lag_pos_max;
+    int mode;
+    if (m < 2LL * nt) mode = C_INV_PAIR_WIN2;
+    else if (m < 4LL * nt) mode = C_INV_PAIR_WIN4;
+    else if (m < 8LL * nt) mode = C_INV_PAIR_WIN8;
+    else return w;
+    if (!get_contig_kernel(pl->logn[last], pl->loge[last], mode).fn) return w;
+    const int wu = window_wu(mode);
+    const long long rows = 1LL << (pl->logL - pl->logn[last]);
+    w.mode = mode;
+    w.slots = 2 * wu * nt;
+    w.rows_per_cta = (int)std::min<long long>(32, std::max<long long>(1, rows / 8));
+    w.n_chunks = (int)(rows / w.rows_per_cta);
+    return w;
+}
+
 extern "C" size_t rmx_plan_workspace_bytes(const rmx_plan* pl, int n_pairs) {
     if (!pl || n_pairs <= 0) return 0;
+    const WindowMode w = window_mode(pl);
+    if (w.mode >= 0) return (size_t)n_pairs * (w.n_chunks + 1) * w.slots * sizeof(float2) + 256;
     const size_t L = size_t(1) << pl->logL;
     return (size_t)n_pairs * (L * sizeof(float2) + (size_t)tiles_per_item_pass0(pl) * sizeof(Partial)) + 256;
+}
+
+extern "C" int rmx_plan_set_search_mode(rmx_plan* pl, int force_full) {
+    if (!pl) return fail(RMX_ERR_ARG, "plan is null");
+    pl->force_full_search = force_full != 0;
+    return RMX_OK;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -393,7 +433,8 @@ __device__ __forceinline__ float parabolic(float ym, float y0, float yp) {
 // n_0-term sums over the input of the outermost inverse pass (still in the workspace).
 __global__ void __launch_bounds__(128) k_finalize_sum(const Partial* __restrict__ partials, int tiles_per_item,
                                                       const float2* __restrict__ D, int logL, int logn0, int logs0,
-                                                      int lag_pos_max, int lag_neg_max, rmx_peak* __restrict__ out) {
+                                                      int lag_pos_max, int lag_neg_max, float scale,
+                                                      rmx_peak* __restrict__ out) {
     __shared__ float s_v[4];
     __shared__ uint32_t s_l[4];
     __shared__ float2 s_sum[4];
@@ -436,7 +477,8 @@ __global__ void __launch_bounds__(128) k_finalize_sum(const Partial* __restrict_
             }
         }
         const float2 tot = block_sum3(acc, s_sum);
-        y[d + 1] = in_range ? sqrtf(tot.x * tot.x + tot.y * tot.y) : -1.f;
+        // the workspace holds the unscaled inner passes; apply the 1/L of the inverse here
+        y[d + 1] = in_range ? sqrtf(tot.x * tot.x + tot.y * tot.y) * scale : -1.f;
     }
     if (threadIdx.x == 0) {
         rmx_peak r;
@@ -492,12 +534,106 @@ __global__ void __launch_bounds__(128) k_finalize_direct(const float2* __restric
     }
 }
 
+// windowed mode, step 1: c[pair][slot] = scale * sum over row chunks of the partial vectors
+__global__ void __launch_bounds__(256) k_window_reduce(const float2* __restrict__ partials, int n_chunks, int slots, float scale,
+                                                       float2* __restrict__ c) {
+    const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx >= slots) return;
+    const float2* __restrict__ base = partials + (long long)blockIdx.y * n_chunks * slots + sidx;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int k = 0; k < n_chunks; ++k) {
+        const float2 v = base[(long long)k * slots];
+        acc.x += v.x; acc.y += v.y;
+    }
+    c[(long long)blockIdx.y * slots + sidx] = make_float2(acc.x * scale, acc.y * scale);
+}
+
+// step 2: arg-max of |c| over |lag| <= M (slot = lag mod slots), parabolic vertex
+__global__ void __launch_bounds__(256) k_finalize_window(const float2* __restrict__ c, int slots, int lag_max,
+                                                         rmx_peak* __restrict__ out) {
+    __shared__ float s_v[8];
+    __shared__ uint32_t s_l[8];
+    const int item = blockIdx.x;
+    const float2* __restrict__ ci = c + (long long)item * slots;
+    float bv = -1.f;
+    uint32_t brank = 0xffffffffu;
+    for (int lag = -lag_max + (int)threadIdx.x; lag <= lag_max; lag += blockDim.x) {
+        const float m2 = cnorm2(ci[lag >= 0 ? lag : lag + slots]);
+        const uint32_t rank = (uint32_t)(lag + lag_max);
+        if (better(m2, rank, bv, brank)) { bv = m2; brank = rank; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const uint32_t ol = __shfl_xor_sync(0xffffffffu, brank, off);
+        if (better(ov, ol, bv, brank)) { bv = ov; brank = ol; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_l[threadIdx.x >> 5] = brank; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bv = s_v[0]; brank = s_l[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) if (better(s_v[w], s_l[w], bv, brank)) { bv = s_v[w]; brank = s_l[w]; }
+        const int blag = (int)brank - lag_max;
+        float y[3];
+        for (int d = -1; d <= 1; ++d) {
+            const int lag = blag + d;
+            if (lag < -lag_max || lag > lag_max) { y[d + 1] = -1.f; continue; }
+            const float2 v = ci[lag >= 0 ? lag : lag + slots];
+            y[d + 1] = sqrtf(cnorm2(v));
+        }
+        rmx_peak r;
+        r.lag = blag;
+        r.peak = y[1];
+        r.frac = (y[0] >= 0.f && y[2] >= 0.f) ? parabolic(y[0], y[1], y[2]) : 0.f;
+        r.pad = bv;
+        out[item] = r;
+    }
+}
+
+static int xcorr_windowed(const rmx_plan* pl, const WindowMode& w, const rmx_complex64* spectra, const rmx_pair* pairs,
+                          int n_pairs, rmx_peak* out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    const size_t per_pair = (size_t)(w.n_chunks + 1) * w.slots * sizeof(float2);
+    if (workspace_bytes < per_pair)
+        return fail(RMX_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one pair (%zu needed)", workspace_bytes, per_pair);
+    const int chunk = (int)std::min<size_t>((size_t)n_pairs, workspace_bytes / per_pair);
+    const int last = pl->n_passes - 1;
+    const KernelEntry k = get_contig_kernel(pl->logn[last], pl->loge[last], w.mode);
+    for (int first = 0; first < n_pairs; first += chunk) {
+        const int cnt = std::min(chunk, n_pairs - first);
+        PassParams pp = base_params(pl);
+        pp.n_items = cnt;
+        pp.spectra = reinterpret_cast<const float2*>(spectra);
+        pp.pairs = reinterpret_cast<const int2*>(pairs) + first;
+        pp.tabs = pl->tabs[last];
+        pp.items_per_cta = w.rows_per_cta;
+        pp.win_partials = reinterpret_cast<float2*>(workspace);
+        pp.win_lag_max = (int)pl->lag_pos_max;
+        pp.row_npass = last;
+        for (int t = 0; t < last; ++t) pp.row_logn[t] = pl->logn[t];
+        int rc = launch_pass(pl, k, "contig_inv_pair_window", dim3((unsigned)cnt * (unsigned)w.n_chunks), pp, st);
+        if (rc) return rc;
+        float2* cvec = pp.win_partials + (size_t)chunk * w.n_chunks * w.slots;      // after the partials
+        {
+            ProfScope prof(pl, "finalize_window", st);
+            k_window_reduce<<<dim3((w.slots + 255) / 256, cnt), 256, 0, st>>>(pp.win_partials, w.n_chunks, w.slots,
+                                                                             1.0f / (float)(size_t(1) << pl->logL), cvec);
+            k_finalize_window<<<cnt, 256, 0, st>>>(cvec, w.slots, (int)pl->lag_pos_max, out + first);
+        }
+        LAUNCH_CHECK("finalize_window");
+    }
+    return RMX_OK;
+}
+
 extern "C" int rmx_xcorr_pairs_peak(const rmx_plan* pl, const rmx_complex64* spectra, const rmx_pair* pairs,
                                     int n_pairs, rmx_peak* out, void* workspace, size_t workspace_bytes,
                                     void* stream) {
     if (!pl || !spectra || !pairs || !out || !workspace) return fail(RMX_ERR_ARG, "null argument to rmx_xcorr_pairs_peak");
     if (n_pairs <= 0) return RMX_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        const WindowMode w = window_mode(pl);
+        if (w.mode >= 0) return xcorr_windowed(pl, w, spectra, pairs, n_pairs, out, workspace, workspace_bytes, st);
+    }
     const size_t L = size_t(1) << pl->logL;
     const int tpi = tiles_per_item_pass0(pl);
     const size_t per_pair = L * sizeof(float2) + (size_t)tpi * sizeof(Partial);
@@ -518,7 +654,10 @@ extern "C" int rmx_xcorr_pairs_peak(const rmx_plan* pl, const rmx_complex64* spe
         pp.src = D;
         pp.dst = D;
         pp.partials = partials;
-        pp.scale = 1.0f / (float)L;
+        const float inv_len = 1.0f / (float)L;
+        // the 1/L of the inverse transform rides on the twiddles of the outermost column pass
+        // (exact: a power of two); single-pass plans scale in the contiguous kernel
+        pp.scale = np == 1 ? inv_len : 1.0f;
         // innermost pass first: rows of X_j * conj(X_i)
         pp.tabs = pl->tabs[np - 1];
         int rc = launch_pass(pl, get_contig_kernel(pl->logn[np - 1], pl->loge[np - 1], C_INV_PAIR), "contig_inv_pair",
@@ -527,6 +666,7 @@ extern "C" int rmx_xcorr_pairs_peak(const rmx_plan* pl, const rmx_complex64* spe
         for (int t = np - 2; t >= 0; --t) {
             pp.tabs = pl->tabs[t];
             pp.logS = pl->logs[t];
+            pp.scale = t == 0 ? inv_len : 1.0f;
             rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], t == 0 ? K_INV_ARGMAX : K_INV),
                              t == 0 ? "col_inv_argmax" : "col_inv", dim3(tiles_of(pl, t, cnt)), pp, st);
             if (rc) return rc;
@@ -541,7 +681,7 @@ extern "C" int rmx_xcorr_pairs_peak(const rmx_plan* pl, const rmx_complex64* spe
             {
                 ProfScope prof(pl, "finalize_sum", st);
                 k_finalize_sum<<<cnt, 128, 0, st>>>(partials, tpi, D, pl->logL, pl->logn[0], pl->logs[0],
-                                                    (int)pl->lag_pos_max, (int)pl->lag_neg_max, out + first);
+                                                    (int)pl->lag_pos_max, (int)pl->lag_neg_max, inv_len, out + first);
             }
             LAUNCH_CHECK("finalize_sum");
         }
@@ -562,13 +702,15 @@ extern "C" int rmx_xcorr_full(const rmx_plan* pl, const rmx_complex64* spectra, 
     pp.pairs = reinterpret_cast<const int2*>(pairs);
     pp.src = reinterpret_cast<const float2*>(out);
     pp.dst = reinterpret_cast<float2*>(out);
-    pp.scale = 1.0f / (float)(size_t(1) << pl->logL);
+    const float inv_len = 1.0f / (float)(size_t(1) << pl->logL);
+    pp.scale = np == 1 ? inv_len : 1.0f;
     pp.tabs = pl->tabs[np - 1];
     int rc = launch_pass(pl, get_contig_kernel(pl->logn[np - 1], pl->loge[np - 1], C_INV_PAIR), "contig_inv_pair",
                          dim3(tiles_of(pl, np - 1, n_pairs)), pp, st);
     for (int t = np - 2; rc == RMX_OK && t >= 0; --t) {
         pp.tabs = pl->tabs[t];
         pp.logS = pl->logs[t];
+        pp.scale = t == 0 ? inv_len : 1.0f;
         rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], K_INV), "col_inv", dim3(tiles_of(pl, t, n_pairs)), pp, st);
     }
     return rc;

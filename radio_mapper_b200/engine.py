@@ -121,6 +121,10 @@ class Plan:
         self.max_lag = None if max_lag is None else int(max_lag)
         _native.check(_lib.rmx_plan_set_max_lag(self._h, -1 if max_lag is None else int(max_lag)), "rmx_plan_set_max_lag")
 
+    def set_search_mode(self, force_full: bool):
+        """force_full=True disables the one-pass windowed search (full inverse + masked arg-max)."""
+        _native.check(_lib.rmx_plan_set_search_mode(self._h, int(bool(force_full))), "rmx_plan_set_search_mode")
+
     # ---- stages --------------------------------------------------------------------------
     def forward(self, iq_u8: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """cu8[n_signals, 2N] -> spectra complex64[n_signals, L] in the plan layout.

@@ -150,6 +150,39 @@ def test_xcorr_max_lag_window(rmx, max_lag):
     assert np.array_equal(full["lag"], oracle.xcorr_pairs_peak(iq)["lag"])
 
 
+@pytest.mark.parametrize("log_n,max_lag", [(15, 342), (16, 0), (16, 5), (16, 342), (16, 511), (16, 512), (16, 2047),
+                                           (16, 2048), (18, 342), (20, 342), (22, 342)])
+def test_xcorr_one_pass_windowed_search(rmx, log_n, max_lag):
+    """max_lag << row length takes the one-pass windowed kernel; it must agree with the oracle and
+    with the full inverse transform + masked arg-max (set_search_mode(force_full=True))."""
+    n = 1 << log_n
+    iq, delays, _ = synth.delayed_buoys(900 + log_n, 4, n, max_delay=300)
+    plan = rmx.Plan(4, n)
+    S = plan.forward(_cuda(iq))
+    pairs = _cuda(rmx.pair_table(4))
+    plan.set_max_lag(max_lag)
+    got = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, pairs))
+    plan.set_search_mode(True)
+    full = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, pairs))
+    plan.set_search_mode(False)
+    assert np.array_equal(got["lag"], full["lag"])
+    assert np.max(np.abs(got["peak"] / full["peak"] - 1)) <= PEAK_RTOL
+    assert np.max(np.abs(got["frac"] - full["frac"])) <= FRAC_ATOL
+    if log_n <= 20:
+        ref = oracle.xcorr_pairs_peak(iq, max_lag=max_lag)
+        assert np.array_equal(got["lag"], ref["lag"])
+        assert np.max(np.abs(got["peak"] / ref["peak"] - 1)) <= PEAK_RTOL
+        assert np.max(np.abs(got["frac"] - ref["frac"])) <= FRAC_ATOL
+    if max_lag >= 600:
+        assert list(got["lag"]) == [delays[j] - delays[i] for i, j in oracle.pair_list(4)]
+    # the windowed path needs (much) less workspace than the full one
+    if 0 < max_lag < 2048 and log_n >= 16:
+        small = plan.workspace_bytes(6)
+        plan.set_search_mode(True)
+        assert small < plan.workspace_bytes(6)
+        plan.set_search_mode(False)
+
+
 def test_xcorr_edge_inputs(rmx):
     """Saturated / constant inputs and peaks on the edge of the lag range."""
     n = 4096

@@ -9,8 +9,11 @@ from radio_mapper_b200 import engine, synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 N = 1 << (int(sys.argv[2]) if len(sys.argv) > 2 else 20)
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+max_lag = int(sys.argv[4]) if len(sys.argv) > 4 else -1
 iq, delays = synth.delayed_buoys_torch(7, B, 1, N, torch.device("cuda"))
 plan = engine.Plan(B, N)
+if max_lag >= 0:
+    plan.set_max_lag(max_lag)
 pairs_h = engine.pair_table(B)
 pairs = torch.from_numpy(pairs_h).cuda()
 for _ in range(iters):
