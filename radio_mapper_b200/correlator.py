@@ -46,14 +46,16 @@ class Correlator:
         self.spectra = torch.empty((self.n_buoys, self.plan.fft_len), dtype=torch.complex64, device=self.device)
         self.workspace_pairs = workspace_pairs
         self._staging: Optional[torch.Tensor] = None
+        self._copy_stream = None
         self.launches = 0            # kernels launched by the last run()
 
     # -- device-resident core ---------------------------------------------------------------
     def run_device(self, iq_dev: torch.Tensor, windows, pair_slice: Optional[slice] = None,
-                   records: Optional[torch.Tensor] = None, energy: Optional[torch.Tensor] = None):
+                   records: Optional[torch.Tensor] = None, energy: Optional[torch.Tensor] = None, pairs=None):
         """iq_dev: CUDA uint8[B, W, 2N].  Processes the listed windows; returns (records int32
         [len(windows), P', 4], energy uint64[len(windows), B]) on the device."""
-        pairs = self.pairs if pair_slice is None else self.pairs[pair_slice].contiguous()
+        if pairs is None:
+            pairs = self.pairs if pair_slice is None else self.pairs[pair_slice].contiguous()
         nw = len(windows)
         if records is None:
             records = torch.empty((nw, pairs.shape[0], 4), dtype=torch.int32, device=self.device)
@@ -85,22 +87,40 @@ class Correlator:
         windows, pair_slice = sharding.shard_units(n_windows, self.n_pairs, world, rank)
         with torch.cuda.device(self.device):
             if iq_u8.is_cuda:
-                iq_dev = iq_u8
+                rec_dev, en_dev = self.run_device(iq_u8, windows, pair_slice)
             else:
-                if self._staging is None or self._staging.shape != iq_u8.shape:
-                    self._staging = torch.empty(iq_u8.shape, dtype=torch.uint8, device=self.device)
-                if len(windows) == n_windows:
-                    self._staging.copy_(iq_u8, non_blocking=True)
-                else:
-                    for w in windows:                      # copy only this rank's windows
-                        self._staging[:, w, :].copy_(iq_u8[:, w, :], non_blocking=True)
-                iq_dev = self._staging
-            rec_dev, en_dev = self.run_device(iq_dev, windows, pair_slice)
+                rec_dev, en_dev = self._run_from_host(iq_u8, windows, pair_slice)
             if world > 1:
                 rec_dev, en_dev = sharding.gather_records(rec_dev, en_dev, n_windows, self.n_pairs, world, rank)
             rec = rec_dev.cpu().numpy()
             en = en_dev.cpu().numpy()
         return self._finish(rec, en)
+
+    def _run_from_host(self, iq_u8: torch.Tensor, windows, pair_slice):
+        """Host cu8 -> device, one window at a time on a copy stream, so the H2D transfer of window
+        w+1 overlaps the FFT / correlate kernels of window w (pinned host memory makes the copies
+        asynchronous; pageable memory still works, just without overlap)."""
+        if self._staging is None or self._staging.shape != iq_u8.shape:
+            self._staging = torch.empty(iq_u8.shape, dtype=torch.uint8, device=self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        compute = torch.cuda.current_stream()
+        pairs = self.pairs if pair_slice is None else self.pairs[pair_slice].contiguous()
+        records = torch.empty((len(windows), pairs.shape[0], 4), dtype=torch.int32, device=self.device)
+        energy = torch.empty((len(windows), self.n_buoys), dtype=torch.int64, device=self.device)
+        self._copy_stream.wait_stream(compute)              # staging may still be read by earlier kernels
+        events = []
+        with torch.cuda.stream(self._copy_stream):
+            for w in windows:
+                for b in range(self.n_buoys):               # contiguous rows: plain async memcpys
+                    self._staging[b, w].copy_(iq_u8[b, w], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                events.append(ev)
+        for k, w in enumerate(windows):
+            compute.wait_event(events[k])
+            self.run_device(self._staging, [w], pair_slice, records=records[k:k + 1], energy=energy[k:k + 1], pairs=pairs)
+        return records, energy
 
     def _finish(self, rec: np.ndarray, energy_x4: np.ndarray) -> np.ndarray:
         out = np.empty(rec.shape[:2], dtype=RECORD_DTYPE)

@@ -23,8 +23,15 @@ constexpr int kMaxStages = 4;
 // ---------------------------------------------------------------------------------------
 // small complex helpers
 // ---------------------------------------------------------------------------------------
+// Blackwell (sm_100) packed fp32x2 arithmetic: one FADD2 / FFMA2 instruction per complex add / sub
+// halves the issue slots of the butterfly adds (the kernels are issue-bound, not FMA-pipe-bound).
+#ifndef RMX_NO_PACKED_F32X2
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
