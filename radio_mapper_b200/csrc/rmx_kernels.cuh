@@ -114,8 +114,13 @@ __device__ __forceinline__ void block_argmax(float& v, uint32_t& rank, RankOf ra
 // ---------------------------------------------------------------------------------------
 // contiguous pass: FFTs over rows of n consecutive elements
 // ---------------------------------------------------------------------------------------
+// resident CTAs per SM the register allocator must leave room for: 32 values per thread need
+// ~128 registers (2 CTAs), 16 values per thread fit in 80 (3 CTAs)
+__host__ __device__ constexpr int min_ctas(int loge) { return loge >= 5 ? 2 : 3; }
+
 template <int LOGN, int LOGE, int MODE>
-__global__ void __launch_bounds__(kThreads) k_contig(const PassParams p) {
+__global__ void __launch_bounds__(kThreads, (MODE == 3 /* C_FWD_PSD keeps E accumulators */ || MODE >= 4) ? 2 : min_ctas(LOGE))
+k_contig(const PassParams p) {
     using GEO = TileGeom<LOGN, LOGE, false>;
     constexpr int E = GEO::E, NT = GEO::NT, G = GEO::G;
     constexpr bool INV = (MODE == C_INV_PAIR || window_wu(MODE) > 0);
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(kThreads) k_contig(const PassParams p) {
 // column pass: FFTs of length n at element stride s = 2^logS, G adjacent columns per tile
 // ---------------------------------------------------------------------------------------
 template <int LOGN, int LOGE, int MODE>
-__global__ void __launch_bounds__(kThreads) k_col(const PassParams p) {
+__global__ void __launch_bounds__(kThreads, min_ctas(LOGE)) k_col(const PassParams p) {
     using GEO = TileGeom<LOGN, LOGE, true>;
     constexpr int E = GEO::E, NT = GEO::NT, G = GEO::G, LOGG = GEO::LOGG;
     constexpr bool INV = (MODE == K_INV || MODE == K_INV_ARGMAX);
