@@ -222,7 +222,7 @@ class Plan:
                           "rmx_xcorr_full")
         return out
 
-    def welch_psd(self, iq_u8: torch.Tensor, sample_rate: float, segments_in_flight: int = 64) -> torch.Tensor:
+    def welch_psd(self, iq_u8: torch.Tensor, sample_rate: float, segments_in_flight: int = 256) -> torch.Tensor:
         """Welch PSD of n_signals segments of nperseg = fft_len samples each (float32[L], natural order)."""
         _require_cuda(iq_u8, torch.uint8, "iq_u8")
         if self.n_samples != self.fft_len:

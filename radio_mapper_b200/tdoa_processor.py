@@ -17,7 +17,6 @@ from __future__ import annotations
 import itertools
 import logging
 import math
-from collections import Counter
 from dataclasses import dataclass
 from datetime import datetime, timezone
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -76,6 +75,12 @@ class TriangulationResult:
     contributing_buoys: List[str]
     tdoa_measurements: List[TDoAMeasurement]
     method: str
+
+    @property
+    def accuracy_estimate_meters(self) -> float:
+        """Name `central_processor.py:434` reads (the reference dataclass lacks it, so its live
+        triangulation path raises AttributeError)."""
+        return self.accuracy_meters
 
 
 # ----------------------------------------------------------------------------------------
@@ -241,6 +246,51 @@ class HyperbolicPositioning:
             return None
 
 
+    def triangulate_position_robust(self, measurements: List[TDoAMeasurement],
+                                    buoy_positions: Dict[str, BuoyPosition]) -> Optional[TriangulationResult]:
+        """Same model as `triangulate_position`, solved as a scaled least-squares problem in a
+        local east/north/up frame centred on the buoys.  The reference's BFGS works
+        on raw ECEF coordinates (~6.4e6 m) and stops on precision loss in most geometries
+        (Documents/TDOA_README.md:49-52); this variant is offered beside it, not instead of it."""
+        if len(measurements) < 2:
+            return None
+        involved = sorted({b for m in measurements for b in (m.buoy1_id, m.buoy2_id)})
+        if len(involved) < 3 or any(b not in buoy_positions for b in involved):
+            return None
+        ecef = {b: np.array(GeodeticCalculator.lat_lng_to_xyz(buoy_positions[b].lat, buoy_positions[b].lng,
+                                                              buoy_positions[b].altitude)) for b in involved}
+        origin = np.mean(list(ecef.values()), axis=0)
+        up = origin / np.linalg.norm(origin)
+        east = np.cross([0.0, 0.0, 1.0], up)
+        east /= np.linalg.norm(east)
+        north = np.cross(up, east)
+        frame = np.stack([east, north, up])                       # rows: local axes
+        local = {b: frame @ (p - origin) for b, p in ecef.items()}
+        p1 = np.array([local[m.buoy1_id] for m in measurements])
+        p2 = np.array([local[m.buoy2_id] for m in measurements])
+        dd = np.array([m.distance_difference_m for m in measurements])
+        wgt = 1.0 / np.sqrt(np.array([m.confidence for m in measurements]) + 0.1)
+        height = float(np.mean([q[2] for q in local.values()]))
+
+        def residuals(xy):
+            x = np.array([xy[0], xy[1], height])
+            return (np.linalg.norm(x - p2, axis=1) - np.linalg.norm(x - p1, axis=1) - dd) * wgt
+
+        sol = scipy.optimize.least_squares(residuals, [0.0, 0.0], x_scale=1000.0, method="lm" if len(dd) >= 2 else "trf")
+        if not sol.success:
+            return None
+        xyz = origin + frame.T @ np.array([sol.x[0], sol.x[1], height])
+        lat, lng, alt = GeodeticCalculator.xyz_to_lat_lng(*xyz)
+        cost = float(np.sum(sol.fun ** 2))
+        return TriangulationResult(
+            estimated_lat=lat, estimated_lng=lng, estimated_altitude=alt,
+            accuracy_meters=math.sqrt(cost / len(measurements)),
+            confidence=sum(m.confidence for m in measurements) / len(measurements),
+            frequency_mhz=measurements[0].frequency_mhz, signal_type="unknown",
+            timestamp_utc=datetime.now(timezone.utc).isoformat(), contributing_buoys=list(involved),
+            tdoa_measurements=measurements, method="least_squares_enu")
+
+
 # ----------------------------------------------------------------------------------------
 # processor
 # ----------------------------------------------------------------------------------------
@@ -288,6 +338,12 @@ class TDoAProcessor:
                 self.logger.warning("EMERGENCY SIGNAL TRIANGULATED: %s MHz at (%.6f, %.6f) +-%.1fm", frequency,
                                     fix.estimated_lat, fix.estimated_lng, fix.accuracy_meters)
         return results
+
+    def triangulate_signal(self, detections: List[SignalDetection]) -> Optional[TriangulationResult]:
+        """Entry point `central_processor.py:418` calls (missing in the reference): the first
+        triangulation result of `process_signal_detections`, or None."""
+        results = self.process_signal_detections(detections)
+        return results[0] if results else None
 
     def _group_by_frequency(self, detections: List[SignalDetection],
                             frequency_tolerance_mhz: float = 0.01) -> Dict[float, List[SignalDetection]]:
@@ -366,14 +422,17 @@ class TDoAProcessor:
 
     def triangulate_iq(self, iq_u8, buoy_ids: Sequence[str], sample_rate: float = 2048000,
                        frequency_mhz: float = 0.0, signal_type: str = "unknown",
-                       max_lag: Optional[int] = None) -> List[Optional[TriangulationResult]]:
-        """correlate_iq + host multilateration, one result (or None) per window."""
+                       max_lag: Optional[int] = None, robust: bool = False) -> List[Optional[TriangulationResult]]:
+        """correlate_iq + host multilateration, one result (or None) per window.  robust=True uses
+        `triangulate_position_robust` instead of the reference's BFGS."""
         meas = self.correlate_iq(iq_u8, buoy_ids, sample_rate, frequency_mhz, max_lag=max_lag)
+        solve = self.hyperbolic_positioner.triangulate_position_robust if robust else \
+            self.hyperbolic_positioner.triangulate_position
         per_window = len(meas) // max(1, (len(buoy_ids) * (len(buoy_ids) - 1)) // 2)
         n_pairs = len(meas) // max(1, per_window)
         fixes = []
         for w in range(per_window):
-            fix = self.hyperbolic_positioner.triangulate_position(meas[w * n_pairs:(w + 1) * n_pairs], self.buoy_positions)
+            fix = solve(meas[w * n_pairs:(w + 1) * n_pairs], self.buoy_positions)
             if fix is not None:
                 fix.signal_type = signal_type
             fixes.append(fix)

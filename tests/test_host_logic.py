@@ -123,3 +123,30 @@ def test_pair_table_order():
     assert engine.pair_table(4).tolist() == [list(p) for p in oracle.pair_list(4)]
     assert engine.correlation_fft_len(2048000) == 1 << 22 and engine.correlation_fft_len(1 << 20) == 1 << 21
     assert engine.correlation_fft_len(3) == 16
+
+
+def test_triangulate_signal_seam_and_robust_solver(golden):
+    """The entry point central_processor.py:418 calls exists, returns accuracy_estimate_meters, and
+    the ENU least-squares solver recovers the transmitter where the timestamps are exact."""
+    proc, _ = _setup(golden)
+    s = golden["solve"]
+    dets = [T.SignalDetection(bid, 121.5, -55.0, "2025-01-01T00:00:00Z", ts, 0.0, 0.0, 0.9, "emergency")
+            for bid, ts in s["detections"]]
+    r = proc.triangulate_signal(dets)
+    assert r is not None and r.accuracy_estimate_meters == r.accuracy_meters
+    assert proc.triangulate_signal(dets[:2]) is None
+    meas = proc.tdoa_calculator.calculate_tdoa_measurements(dets, proc.buoy_positions)
+    rob = proc.hyperbolic_positioner.triangulate_position_robust(meas, proc.buoy_positions)
+    assert rob is not None and rob.method == "least_squares_enu"
+    G = T.GeodeticCalculator
+    _, err = G.bearing_distance(rob.estimated_lat, rob.estimated_lng, s["tx"][0], s["tx"][1])
+    assert err < 5.0, err                     # metres; timestamps are quantised to 1 ns (0.3 m)
+    # noisy timestamps (1 us): still lands within a few hundred metres
+    rng = np.random.default_rng(0)
+    noisy = [T.SignalDetection(d.buoy_id, d.frequency_mhz, d.signal_strength_dbm, d.timestamp_utc,
+                               d.gps_timestamp_ns + int(rng.integers(-1000, 1001)), d.lat, d.lng, d.confidence, d.signal_type)
+             for d in dets]
+    rob2 = proc.hyperbolic_positioner.triangulate_position_robust(
+        proc.tdoa_calculator.calculate_tdoa_measurements(noisy, proc.buoy_positions), proc.buoy_positions)
+    _, err2 = G.bearing_distance(rob2.estimated_lat, rob2.estimated_lng, s["tx"][0], s["tx"][1])
+    assert err2 < 1500.0, err2
