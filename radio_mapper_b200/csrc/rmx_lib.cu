@@ -212,7 +212,7 @@ struct WindowMode {
     int n_chunks = 0;
 };
 
-static WindowMode window_mode(const rmx_plan* pl) {
+static WindowMode window_mode(const rmx_plan* pl, int n_pairs) {
     WindowMode w;
     if (pl->force_full_search || pl->n_passes < 2 || pl->lag_pos_max != pl->lag_neg_max) return w;
     const int last = pl->n_passes - 1;
@@ -229,14 +229,17 @@ static WindowMode window_mode(const rmx_plan* pl) {
     const long long rows = 1LL << (pl->logL - pl->logn[last]);
     w.mode = mode;
     w.slots = 2 * wu * nt;
-    w.rows_per_cta = (int)std::min<long long>(32, std::max<long long>(1, rows / 8));
+    // rows per CTA: as many as keep >= ~8 CTAs per SM in flight (few pairs -> short chunks), at most 32
+    long long rpc = 32;
+    while (rpc > 1 && (rows / rpc) * (long long)std::max(1, n_pairs) < 148LL * 8) rpc >>= 1;
+    w.rows_per_cta = (int)std::min<long long>(rpc, std::max<long long>(1, rows));
     w.n_chunks = (int)(rows / w.rows_per_cta);
     return w;
 }
 
 extern "C" size_t rmx_plan_workspace_bytes(const rmx_plan* pl, int n_pairs) {
     if (!pl || n_pairs <= 0) return 0;
-    const WindowMode w = window_mode(pl);
+    const WindowMode w = window_mode(pl, n_pairs);
     if (w.mode >= 0) return (size_t)n_pairs * (w.n_chunks + 1) * w.slots * sizeof(float2) + 256;
     const size_t L = size_t(1) << pl->logL;
     return (size_t)n_pairs * (L * sizeof(float2) + (size_t)tiles_per_item_pass0(pl) * sizeof(Partial)) + 256;
@@ -631,7 +634,7 @@ extern "C" int rmx_xcorr_pairs_peak(const rmx_plan* pl, const rmx_complex64* spe
     if (n_pairs <= 0) return RMX_OK;
     cudaStream_t st = (cudaStream_t)stream;
     {
-        const WindowMode w = window_mode(pl);
+        const WindowMode w = window_mode(pl, n_pairs);
         if (w.mode >= 0) return xcorr_windowed(pl, w, spectra, pairs, n_pairs, out, workspace, workspace_bytes, st);
     }
     const size_t L = size_t(1) << pl->logL;

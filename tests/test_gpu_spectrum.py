@@ -212,6 +212,43 @@ def test_stream_detector_matches_reference_golden(golden_dir):
     assert same_bw >= 0.98 * len(want)
 
 
+def test_non_power_of_two_blocks_and_files(tmp_path):
+    """Arbitrary block lengths (the reference FFTs whatever it is given) go through Bluestein."""
+    from radio_mapper_b200 import signal_analyzer as sa
+    from radio_mapper_b200.detectors import BuoySignalDetector, StreamSignalDetector
+    n = 10000
+    iq, bins = synth.tones_block(77, n)
+    x = oracle.unpack_cu8(iq)
+    p = oracle.spectrum_db(oracle.forward_fft(x))
+    # stream detector
+    peaks = oracle.detect_peaks_fixed(p)
+    want = oracle.score_peaks_stream(p, peaks, oracle.freq_axis_hz(n, 2048000, 100e6), 2048000)
+    kbins, got = StreamSignalDetector("N").detect_signals_indexed(x, 100e6)
+    assert len(set(kbins) ^ set(map(int, peaks))) <= 2
+    wb = {w["index"]: w for w in want}
+    for k, d in zip(kbins, got):
+        if k in wb:
+            assert abs(float(d.signal_strength_dbm) - wb[k]["signal_strength_dbm"]) <= 2e-3
+            assert d.signal_type == wb[k]["signal_type"]
+    # buoy detector straight from bytes
+    fc_hz = int(121.5 * 1e6)
+    ora = oracle.score_peaks_buoy(p, peaks, oracle.freq_axis_hz(n, 2048000, fc_hz), fc_hz)
+    bbins, bgot = BuoySignalDetector("B").detect_block_indexed(iq, 121.5)
+    assert len(set(bbins) ^ {o["index"] for o in ora}) <= max(2, len(ora) // 100)
+    # whole-file analysis of a capture whose length is not a power of two
+    path = tmp_path / "iq_capture_100.0MHz_20250101.bin"
+    big, _ = synth.tones_block(78, 250_000)
+    big.tofile(path)
+    res = sa.SignalAnalyzer(verbose=False).analyze_iq_file(str(path), plot=False)
+    xb = oracle.unpack_cu8(big)
+    freqs, pdb, peak_freqs = oracle.analyze_spectrum(xb, 2048000, 100.0)
+    assert res["center_freq_mhz"] == 100.0 and res["stats"]["num_samples"] == 250_000
+    got_bins = np.searchsorted(freqs, res["peak_frequencies"])
+    want_bins = np.searchsorted(freqs, peak_freqs)
+    _same_peaks(got_bins, want_bins, pdb, float(np.mean(pdb) + 10), tol=2e-3)
+    assert abs(res["stats"]["power_db"] - oracle.signal_stats(xb)["power_db"]) < 1e-4
+
+
 def test_correlate_iq_end_to_end():
     import torch
     from radio_mapper_b200.tdoa_processor import TDOAProcessor, BuoyPosition
