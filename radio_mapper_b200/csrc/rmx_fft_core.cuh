@@ -186,14 +186,21 @@ __device__ __forceinline__ void fft_tile(float2 (&r)[GEO::E], float2* smem, int 
         constexpr int NB = E / R;                 // butterflies per thread in this stage
         constexpr int T = 1 << (LOGN - LOGR);     // butterflies per FFT in this stage
         constexpr int P = 1 << LOGP;
+        // Shared-memory addressing: element (g, pos) lives at unit*(pos + (pos >> LOGR0)) (+ g terms).
+        // Every stride used below (T, P) is a multiple of 2^LOGR0 or the stage-0 row stride, so
+        // pad(base + q*stride) == pad(base) + q*pad(stride): one address per butterfly, the rest
+        // are compile-time immediates.
+        constexpr int UNIT = GEO::COLUMN ? GEO::G : 1;
         if constexpr (S > 0) {
+            static_assert(T % (1 << GEO::LOGR0) == 0, "stage stride must keep the padding additive");
+            constexpr int TSTEP = (T + (T >> GEO::LOGR0)) * UNIT;
             // gather this stage's inputs: x[i + q*T]
             static_for<0, NB>([&](auto B_) {
                 constexpr int b = decltype(B_)::value;
-                const int i = i0 + b * NT;
+                const float2* __restrict__ src = smem + GEO::saddr(g, i0 + b * NT);
                 static_for<0, R>([&](auto Q_) {
                     constexpr int q = decltype(Q_)::value;
-                    r[b + q * NB] = smem[GEO::saddr(g, i + q * T)];
+                    r[b + q * NB] = src[q * TSTEP];
                 });
             });
             // twiddle by w_{P*R}^{q*k}, k = i mod P
@@ -219,14 +226,18 @@ __device__ __forceinline__ void fft_tile(float2 (&r)[GEO::E], float2* smem, int 
         });
         if constexpr (S + 1 < GEO::NSTAGES) {
             if constexpr (S > 0) __syncthreads();      // everyone has finished reading the previous exchange
+            static_assert(P == 1 || P % (1 << GEO::LOGR0) == 0, "stage stride must keep the padding additive");
+            // P == 1 (stage 0): jbase = i*R with R == 2^LOGR0, so pad(jbase + q) = pad(jbase) + q
+            constexpr int PSTEP = (P + (P >> GEO::LOGR0)) * UNIT;
             static_for<0, NB>([&](auto B_) {
                 constexpr int b = decltype(B_)::value;
                 const int i = i0 + b * NT;
                 const int k = i & (P - 1);
                 const int jbase = ((i >> LOGP) << (LOGP + LOGR)) | k;
+                float2* __restrict__ dst = smem + GEO::saddr(g, jbase);
                 static_for<0, R>([&](auto Q_) {
                     constexpr int q = decltype(Q_)::value;
-                    smem[GEO::saddr(g, jbase + q * P)] = r[b + q * NB];
+                    dst[q * PSTEP] = r[b + q * NB];
                 });
             });
             __syncthreads();
