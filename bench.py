@@ -57,48 +57,63 @@ def measured_peak():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 50 ms from before the warm-up until after the timed region; the
+    summary uses the samples whose timestamps fall inside the timed region (falling back to every
+    sample taken under load if the region was shorter than the sampling period)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_indices):
         self.idx = set(int(i) for i in gpu_indices)
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, pw, reasons = [], [], [], set()
+        import datetime
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 8 or not f[0].isdigit() or int(f[0]) not in self.idx:
+            if len(f) < 9 or not f[1].isdigit() or int(f[1]) not in self.idx:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[2]), float(f[3]), float(f[4]), [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.05 <= r[0] <= self.t1 + 0.05]
+        scope = "timed region"
+        if len(inside) < 2:
+            loaded = [r for r in rows if r[3] > 250.0]                  # under load (warm-up runs the same kernels)
+            inside, scope = (loaded or rows), "warm-up + timed region (timed region shorter than the sampling period)"
+        if not inside:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        reasons = sorted({n for r in inside for n in r[4]})
+        return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(max(r[2] for r in inside)),
+                "power_w_max": float(max(r[3] for r in inside)), "samples": len(inside), "scope": scope, "reasons": reasons}
 
 
 # ----------------------------------------------------------------------------------------
@@ -196,6 +211,9 @@ def run_b200(args, wl):
             rec, en = sharding.gather_records(rec, en, W * world, P, world, rank)
         return rec, en
 
+    sampler = ClockSampler(range(world) if rank == 0 else [])
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         rec, en = step()
     torch.cuda.synchronize()
@@ -206,12 +224,10 @@ def run_b200(args, wl):
     if not np.array_equal(got, want):
         raise SystemExit("bench: lags do not match the synthetic delays (%d mismatches)" % int((got != want).sum()))
 
-    sampler = ClockSampler(range(world) if rank == 0 else [])
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     plan.profile(True)
     cor.launches = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -220,6 +236,7 @@ def run_b200(args, wl):
         step()
     ev1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     if world > 1:
         dist.barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
