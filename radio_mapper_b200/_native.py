@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librmx.so")
+# RMX_LIB_PATH: developer override used by tools/variant_build.py to A/B kernel build variants
+LIB_PATH = os.environ.get("RMX_LIB_PATH") or os.path.join(_HERE, "librmx.so")
 
 c_void_p, c_int, c_size_t, c_uint, c_float, c_double, c_longlong = (
     ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_uint, ctypes.c_float, ctypes.c_double,

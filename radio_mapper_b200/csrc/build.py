@@ -40,6 +40,22 @@ def _compile(src):
     return obj, r.stderr
 
 
+def build_variant(name, defines, verbose=False):
+    """Developer aid: build radio_mapper_b200/_variants/librmx_<name>.so with extra -D flags (A/B runs
+    through RMX_LIB_PATH).  Objects go to a per-variant directory."""
+    global OBJ, OUT, FLAGS
+    saved = (OBJ, OUT, FLAGS)
+    try:
+        vdir = os.path.join(PKG, "_variants")
+        os.makedirs(vdir, exist_ok=True)
+        OBJ = os.path.join(HERE, "_obj_" + name)
+        OUT = os.path.join(vdir, "librmx_%s.so" % name)
+        FLAGS = FLAGS + ["-D" + d for d in defines]
+        return build(force=False, verbose=verbose)
+    finally:
+        OBJ, OUT, FLAGS = saved
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     if force:
@@ -61,5 +77,9 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(path)
+    if "--variant" in sys.argv:          # python build.py --variant NAME -DX=1 -DY=2
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a[2:] for a in sys.argv[i + 2:] if a.startswith("-D")], verbose="-v" in sys.argv))
+    else:
+        path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+        print(path)

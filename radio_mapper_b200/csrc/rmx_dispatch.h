@@ -12,6 +12,17 @@ struct KernelEntry {
     int logG;           // log2(FFTs per tile)
 };
 
+typedef void (*ArgmaxTmaKernel)(const PassParams, const CUtensorMap, const unsigned);
+struct TmaKernelEntry {
+    ArgmaxTmaKernel fn;  // nullptr if not instantiated
+    size_t smem_bytes;
+    int logG;
+    int box_rows;
+    int ctas_per_sm;     // resident CTAs the kernel was compiled for (grid = this * SM count)
+};
+// persistent TMA-fed arg-max pass (32 values per thread; n = 512 or 1024)
+TmaKernelEntry get_argmax_tma_kernel(int logn, int loge, bool pre_twiddled);
+
 KernelEntry get_contig_kernel(int logn, int loge, int mode);
 KernelEntry get_col_kernel(int logn, int loge, int mode);
 

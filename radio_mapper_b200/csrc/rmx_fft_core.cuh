@@ -173,47 +173,75 @@ struct StageTables {
     const float2* tw[kMaxStages];
 };
 
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+
 // Run all Stockham stages on the register tile.  On entry r[u] = x[i0 + u*NT]; on exit
 // r[u] = X[i0 + u*NT] (natural order).  All 256 threads must call (contains barriers).
-template <class GEO, bool INV>
-__device__ __forceinline__ void fft_tile(float2 (&r)[GEO::E], float2* smem, int g, int i0, const StageTables& tabs) {
+//
+// TWTREE: read only the power-of-two entries of each stage's twiddle table and build the rest.
+// `after_last_gather` runs once every thread's last read of the exchange buffer has been ISSUED;
+// a caller that wants to refill the buffer puts its own barrier inside the hook.
+template <class GEO, bool INV, bool TWTREE = false, class Hook = NoHook>
+__device__ __forceinline__ void fft_tile(float2 (&r)[GEO::E], float2* smem, int g, int i0, const StageTables& tabs,
+                                         Hook after_last_gather = Hook{}) {
     constexpr int E = GEO::E, LOGE = GEO::LOGE, LOGN = GEO::LOGN, NT = GEO::NT;
+    // Shared-memory addressing: element (g, pos) lives at unit*(pos + (pos >> LOGR0)) (+ g terms).
+    // Every stride used below (T, P) is a multiple of 2^LOGR0 or the stage-0 row stride, so
+    // pad(base + q*stride) == pad(base) + q*pad(stride): one address per butterfly, the rest
+    // are compile-time immediates.
+    constexpr int UNIT = GEO::COLUMN ? GEO::G : 1;
     static_for<0, GEO::NSTAGES>([&](auto S_) {
         constexpr int S = decltype(S_)::value;
         constexpr int LOGP = S * LOGE;
         constexpr int LOGR = cmin(LOGE, LOGN - LOGP);
         constexpr int R = 1 << LOGR;
         constexpr int NB = E / R;                 // butterflies per thread in this stage
-        constexpr int T = 1 << (LOGN - LOGR);     // butterflies per FFT in this stage
         constexpr int P = 1 << LOGP;
-        // Shared-memory addressing: element (g, pos) lives at unit*(pos + (pos >> LOGR0)) (+ g terms).
-        // Every stride used below (T, P) is a multiple of 2^LOGR0 or the stage-0 row stride, so
-        // pad(base + q*stride) == pad(base) + q*pad(stride): one address per butterfly, the rest
-        // are compile-time immediates.
-        constexpr int UNIT = GEO::COLUMN ? GEO::G : 1;
         if constexpr (S > 0) {
-            static_assert(T % (1 << GEO::LOGR0) == 0, "stage stride must keep the padding additive");
-            constexpr int TSTEP = (T + (T >> GEO::LOGR0)) * UNIT;
-            // gather this stage's inputs: x[i + q*T]
-            static_for<0, NB>([&](auto B_) {
-                constexpr int b = decltype(B_)::value;
-                const float2* __restrict__ src = smem + GEO::saddr(g, i0 + b * NT);
-                static_for<0, R>([&](auto Q_) {
-                    constexpr int q = decltype(Q_)::value;
-                    r[b + q * NB] = src[q * TSTEP];
-                });
-            });
-            // twiddle by w_{P*R}^{q*k}, k = i mod P
+            // twiddle by w_{P*R}^{q*k}, k = i mod P (the inputs were gathered at the end of stage S-1)
             const float2* __restrict__ tw = tabs.tw[S];
             static_for<0, NB>([&](auto B_) {
                 constexpr int b = decltype(B_)::value;
                 const int k = (i0 + b * NT) & (P - 1);
-                static_for<1, R>([&](auto Q_) {
-                    constexpr int q = decltype(Q_)::value;
-                    float2 w = __ldg(tw + (q - 1) * P + k);
-                    if (INV) w.y = -w.y;
-                    r[b + q * NB] = cmul(r[b + q * NB], w);
-                });
+                if constexpr (TWTREE && LOGR >= 3) {
+                    // Only the power-of-two exponents are read from the table (each correctly rounded);
+                    // the other w^q are products of at most log2(R) of them.  Trades table loads (L1
+                    // wavefronts, long-scoreboard latency after the barrier) for FMA work.
+                    constexpr int LO = 4;                        // w^q = wl[q % LO] * wh[q / LO]
+                    float2 pw[LOGR];
+                    static_for<0, LOGR>([&](auto Z_) {
+                        constexpr int z = decltype(Z_)::value;
+                        pw[z] = __ldg(tw + ((1 << z) - 1) * P + k);
+                        if (INV) pw[z].y = -pw[z].y;
+                    });
+                    float2 wl[LO];
+                    wl[1] = pw[0]; wl[2] = pw[1]; wl[3] = cmul(pw[0], pw[1]);
+                    float2 wh[R / LO];
+                    static_for<1, R / LO>([&](auto M_) {
+                        constexpr int m = decltype(M_)::value;
+                        constexpr int top = ilog2(m + 1) - ((1 << (ilog2(m + 1))) > m ? 1 : 0);   // floor(log2 m)
+                        if constexpr ((m & (m - 1)) == 0) wh[m] = pw[2 + top];
+                        else wh[m] = cmul(wh[m - (1 << top)], pw[2 + top]);
+                    });
+                    static_for<1, R>([&](auto Q_) {
+                        constexpr int q = decltype(Q_)::value;
+                        constexpr int lo = q % LO, hi = q / LO;
+                        float2 w;
+                        if constexpr (hi == 0) w = wl[lo];
+                        else if constexpr (lo == 0) w = wh[hi];
+                        else w = cmul(wl[lo], wh[hi]);
+                        r[b + q * NB] = cmul(r[b + q * NB], w);
+                    });
+                } else {
+                    static_for<1, R>([&](auto Q_) {
+                        constexpr int q = decltype(Q_)::value;
+                        float2 w = __ldg(tw + (q - 1) * P + k);
+                        if (INV) w.y = -w.y;
+                        r[b + q * NB] = cmul(r[b + q * NB], w);
+                    });
+                }
             });
         }
         // R-point DFTs
@@ -225,10 +253,18 @@ __device__ __forceinline__ void fft_tile(float2 (&r)[GEO::E], float2* smem, int 
             static_for<0, R>([&](auto Q_) { constexpr int q = decltype(Q_)::value; r[b + q * NB] = x[q]; });
         });
         if constexpr (S + 1 < GEO::NSTAGES) {
-            if constexpr (S > 0) __syncthreads();      // everyone has finished reading the previous exchange
+            // exchange: scatter this stage's outputs, gather the next stage's inputs x[i + q*T2]
+            constexpr int LOGP2 = LOGP + LOGE;
+            constexpr int LOGR2 = cmin(LOGE, LOGN - LOGP2);
+            constexpr int R2 = 1 << LOGR2;
+            constexpr int NB2 = E / R2;
+            constexpr int T2 = 1 << (LOGN - LOGR2);   // butterflies per FFT in the next stage
             static_assert(P == 1 || P % (1 << GEO::LOGR0) == 0, "stage stride must keep the padding additive");
+            static_assert(T2 % (1 << GEO::LOGR0) == 0, "stage stride must keep the padding additive");
             // P == 1 (stage 0): jbase = i*R with R == 2^LOGR0, so pad(jbase + q) = pad(jbase) + q
             constexpr int PSTEP = (P + (P >> GEO::LOGR0)) * UNIT;
+            constexpr int TSTEP = (T2 + (T2 >> GEO::LOGR0)) * UNIT;
+            if constexpr (S > 0) __syncthreads();      // everyone has finished reading the previous exchange
             static_for<0, NB>([&](auto B_) {
                 constexpr int b = decltype(B_)::value;
                 const int i = i0 + b * NT;
@@ -241,6 +277,15 @@ __device__ __forceinline__ void fft_tile(float2 (&r)[GEO::E], float2* smem, int 
                 });
             });
             __syncthreads();
+            static_for<0, NB2>([&](auto B_) {
+                constexpr int b = decltype(B_)::value;
+                const float2* __restrict__ src = smem + GEO::saddr(g, i0 + b * NT);
+                static_for<0, R2>([&](auto Q_) {
+                    constexpr int q = decltype(Q_)::value;
+                    r[b + q * NB2] = src[q * TSTEP];
+                });
+            });
+            if constexpr (S + 2 == GEO::NSTAGES) after_last_gather();
         }
     });
 }
@@ -291,6 +336,26 @@ __device__ __forceinline__ void row_twiddles(float2 (&tw)[E], uint32_t j, uint32
         constexpr int z = decltype(Z_)::value;
         if constexpr ((z & 1) == 0) pw = unit_root((j * (step_rows << z)) & mask, logm, inverse);
         else pw = make_float2(pw.x * pw.x - pw.y * pw.y, 2.0f * pw.x * pw.y);
+        static_for<0, (1 << z)>([&](auto U_) {
+            constexpr int u = decltype(U_)::value;
+            tw[u + (1 << z)] = cmul(tw[u], pw);
+        });
+    });
+}
+
+// Same result as row_twiddles when the step powers pw[z] = root^(j*step_rows*2^z), z < log2(E), are
+// shared by the whole CTA (one row per tile): they are read from shared memory, each an exactly
+// reduced root, so a thread evaluates one sincospif instead of 1 + log2(E)/2.
+template <int E>
+__device__ __forceinline__ void row_twiddles_shared(float2 (&tw)[E], uint32_t j, uint32_t i0, int logm, bool inverse,
+                                                    float scale, const float2* pw_shared) {
+    const uint32_t mask = (logm >= 32) ? 0xffffffffu : ((1u << logm) - 1u);
+    tw[0] = unit_root((j * i0) & mask, logm, inverse);
+    tw[0].x *= scale;
+    tw[0].y *= scale;
+    static_for<0, ilog2(E)>([&](auto Z_) {
+        constexpr int z = decltype(Z_)::value;
+        const float2 pw = pw_shared[z];
         static_for<0, (1 << z)>([&](auto U_) {
             constexpr int u = decltype(U_)::value;
             tw[u + (1 << z)] = cmul(tw[u], pw);

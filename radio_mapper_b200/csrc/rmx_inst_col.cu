@@ -32,6 +32,8 @@ KernelEntry get_col_kernel(int logn, int loge, int mode) {
         case K_FWD: return col_by_logn<4, K_FWD>(logn);
         case K_INV: return col_by_logn<4, K_INV>(logn);
         case K_INV_ARGMAX: return col_by_logn<4, K_INV_ARGMAX>(logn);
+        case K_INV_PRE: return col_by_logn<4, K_INV_PRE>(logn);
+        case K_INV_ARGMAX_PRE: return col_by_logn<4, K_INV_ARGMAX_PRE>(logn);
         default: return KernelEntry{nullptr, 0, 0};
     }
 }

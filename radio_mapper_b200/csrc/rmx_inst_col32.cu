@@ -25,8 +25,23 @@ KernelEntry get_col_kernel32(int logn, int mode) {
         case K_FWD: return col32_by_logn<K_FWD>(logn);
         case K_INV: return col32_by_logn<K_INV>(logn);
         case K_INV_ARGMAX: return col32_by_logn<K_INV_ARGMAX>(logn);
+        case K_INV_PRE: return col32_by_logn<K_INV_PRE>(logn);
+        case K_INV_ARGMAX_PRE: return col32_by_logn<K_INV_ARGMAX_PRE>(logn);
         default: return KernelEntry{nullptr, 0, 0};
     }
+}
+
+template <int LOGN, bool PRE>
+static TmaKernelEntry tma_entry() {
+    using GEO = TileGeom<LOGN, 5, true>;
+    return TmaKernelEntry{(ArgmaxTmaKernel)k_col_argmax_tma<LOGN, 5, PRE>, GEO::SMEM_BYTES + 128, GEO::LOGG,
+                          GEO::N < 256 ? GEO::N : 256, argmax_tma_ctas(5)};
+}
+
+TmaKernelEntry get_argmax_tma_kernel(int logn, int loge, bool pre) {
+    if (loge == 5 && logn == 10) return pre ? tma_entry<10, true>() : tma_entry<10, false>();
+    if (loge == 5 && logn == 9) return pre ? tma_entry<9, true>() : tma_entry<9, false>();
+    return TmaKernelEntry{nullptr, 0, 0, 0, 0};
 }
 
 }  // namespace rmx

@@ -16,7 +16,21 @@
 //                  INPUT of each column pass; the last pass to run (pass 0) yields natural-order
 //                  lags and is fused with the |c|^2 arg-max.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the driver entry point is resolved at run time)
 #include "rmx_fft_core.cuh"
+
+#ifndef RMX_PAIR_TWTREE
+#define RMX_PAIR_TWTREE 1   // contiguous pair pass: build stage twiddles from their power-of-two entries
+#endif
+#ifndef RMX_PAIR_CTAS
+#define RMX_PAIR_CTAS 2     // resident CTAs per SM requested for the contiguous pair pass (32 values/thread)
+#endif
+#ifndef RMX_ARGMAX_CTAS
+#define RMX_ARGMAX_CTAS 2   // resident CTAs per SM requested for the pre-twiddled arg-max column pass (32 values/thread)
+#endif
+#ifndef RMX_ARGMAX_TMA_CTAS
+#define RMX_ARGMAX_TMA_CTAS 3   // same for the TMA-fed kernel: its tile arrives through shared memory, so 80 registers suffice
+#endif
 
 namespace rmx {
 
@@ -50,6 +64,12 @@ struct PassParams {
     int win_lag_max;          // keep |lag| <= win_lag_max  (< WU*NT)
     int row_npass;            // number of outer (column) passes whose digits make up a row index
     int row_logn[kMaxStages]; // their lengths (log2), outermost first
+    // Inter-pass twiddles of the inverse transform ride on the OUTPUT of the contiguous pass
+    // (C_INV_PAIR), which is bound by shared-memory bandwidth and has FMA slots to spare, instead of
+    // the input of the column pass that follows, which is FMA-bound:
+    int post_logm;            // C_INV_PAIR: log2(M) of the next column pass (0 = do not twiddle)
+    int post_logn;            // C_INV_PAIR: log2 of that pass's transform length (row index = row mod n)
+    float post_scale;         // C_INV_PAIR: scale folded into those twiddles (a power of two)
 };
 
 enum ContigMode { C_FWD = 0, C_FWD_CU8 = 1, C_INV_PAIR = 2, C_FWD_PSD = 3, C_INV_PAIR_WIN2 = 4, C_INV_PAIR_WIN4 = 5, C_INV_PAIR_WIN8 = 6 };
@@ -69,7 +89,8 @@ __device__ __forceinline__ uint32_t row_frequency(const PassParams& p, uint32_t 
     }
     return phi;
 }
-enum ColMode { K_FWD_CU8 = 0, K_FWD = 1, K_INV = 2, K_INV_ARGMAX = 3 };
+// *_PRE: the input already carries this pass's twiddles and scale (applied by the contiguous pass)
+enum ColMode { K_FWD_CU8 = 0, K_FWD = 1, K_INV = 2, K_INV_ARGMAX = 3, K_INV_PRE = 4, K_INV_ARGMAX_PRE = 5 };
 
 __device__ __forceinline__ float2 load_cu8_sample(const uint8_t* base, long long idx) {
     // (float)u8 - 127.5f, I then Q: exactly the reference's unpack (buoy_node.py:392-398)
@@ -117,9 +138,10 @@ __device__ __forceinline__ void block_argmax(float& v, uint32_t& rank, RankOf ra
 // resident CTAs per SM the register allocator must leave room for: 32 values per thread need
 // ~128 registers (2 CTAs), 16 values per thread fit in 80 (3 CTAs)
 __host__ __device__ constexpr int min_ctas(int loge) { return loge >= 5 ? 2 : 3; }
+__host__ __device__ constexpr int argmax_tma_ctas(int loge) { return loge >= 5 ? RMX_ARGMAX_TMA_CTAS : 4; }
 
 template <int LOGN, int LOGE, int MODE>
-__global__ void __launch_bounds__(kThreads, (MODE == 3 /* C_FWD_PSD keeps E accumulators */ || MODE >= 4) ? 2 : min_ctas(LOGE))
+__global__ void __launch_bounds__(kThreads, (MODE == 3 /* C_FWD_PSD keeps E accumulators */ || MODE >= 4) ? 2 : (MODE == 2 && LOGE == 5) ? RMX_PAIR_CTAS : min_ctas(LOGE))
 k_contig(const PassParams p) {
     using GEO = TileGeom<LOGN, LOGE, false>;
     constexpr int E = GEO::E, NT = GEO::NT, G = GEO::G;
@@ -232,6 +254,14 @@ k_contig(const PassParams p) {
             row = flat & ((1LL << log_rows) - 1);
         }
         const bool active = item < p.n_items;
+        __shared__ float2 s_pw[8];
+        if constexpr (MODE == C_INV_PAIR && G == 1) {
+            if (p.post_logm > 0 && threadIdx.x < LOGE) {
+                const uint32_t rr = (uint32_t)row & ((1u << p.post_logn) - 1u);
+                const uint32_t mask = (p.post_logm >= 32) ? 0xffffffffu : ((1u << p.post_logm) - 1u);
+                s_pw[threadIdx.x] = unit_root((rr * ((uint32_t)NT << threadIdx.x)) & mask, p.post_logm, true);
+            }
+        }
 
         if constexpr (MODE == C_FWD) {
             const float2* __restrict__ in = p.src + item * p.src_item_stride + (row << LOGN);
@@ -261,9 +291,24 @@ k_contig(const PassParams p) {
             }
         }
 
-        fft_tile<GEO, INV>(r, smem, g, i0, p.tabs);
+        fft_tile<GEO, INV, (MODE == C_INV_PAIR && RMX_PAIR_TWTREE != 0)>(r, smem, g, i0, p.tabs);
 
         if constexpr (MODE == C_INV_PAIR) {
+            if (p.post_logm > 0) {
+                // input twiddles w_M^{+r*j} of the column pass that consumes this row (r = row within
+                // its block, j = column = position in the row), times its scale
+                const uint32_t rr = (uint32_t)row & ((1u << p.post_logn) - 1u);
+                float2 tw[E];
+                if constexpr (G == 1) {
+                    // the step powers w_M^{r*NT*2^z} are the same for the whole CTA: s_pw was filled
+                    // before the first barrier of fft_tile
+                    row_twiddles_shared<E>(tw, rr, (uint32_t)i0, p.post_logm, true, p.post_scale, s_pw);
+                } else {
+                    row_twiddles<E>(tw, rr, (uint32_t)i0, (uint32_t)NT, p.post_logm, true, p.post_scale);
+                }
+#pragma unroll
+                for (int u = 0; u < E; ++u) r[u] = cmul(r[u], tw[u]);
+            }
             // single-pass plans apply the 1/L here; multi-pass plans fold it into the twiddles of
             // the outermost column pass (p.scale == 1 for this launch)
             if (p.scale != 1.0f) {
@@ -283,10 +328,12 @@ k_contig(const PassParams p) {
 // column pass: FFTs of length n at element stride s = 2^logS, G adjacent columns per tile
 // ---------------------------------------------------------------------------------------
 template <int LOGN, int LOGE, int MODE>
-__global__ void __launch_bounds__(kThreads, min_ctas(LOGE)) k_col(const PassParams p) {
+__global__ void __launch_bounds__(kThreads, (MODE == K_INV_ARGMAX_PRE && LOGE == 5) ? RMX_ARGMAX_CTAS : min_ctas(LOGE)) k_col(const PassParams p) {
     using GEO = TileGeom<LOGN, LOGE, true>;
     constexpr int E = GEO::E, NT = GEO::NT, G = GEO::G, LOGG = GEO::LOGG;
-    constexpr bool INV = (MODE == K_INV || MODE == K_INV_ARGMAX);
+    constexpr bool INV = (MODE == K_INV || MODE == K_INV_ARGMAX || MODE == K_INV_PRE || MODE == K_INV_ARGMAX_PRE);
+    constexpr bool PRE = (MODE == K_INV_PRE || MODE == K_INV_ARGMAX_PRE);
+    constexpr bool ARGMAX = (MODE == K_INV_ARGMAX || MODE == K_INV_ARGMAX_PRE);
     extern __shared__ float2 smem[];
 
     int g, i0;
@@ -362,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(LOGE)) k_col(const PassPara
         for (int u = 0; u < E; ++u) { r[u] = *in; in += rstride; }
     }
 
-    if constexpr (INV) {
+    if constexpr (INV && !PRE) {
         float2 tw[E];
         row_twiddles<E>(tw, j, (uint32_t)i0, (uint32_t)NT, logM, true, p.scale);
 #pragma unroll
@@ -378,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(LOGE)) k_col(const PassPara
         for (int u = 0; u < E; ++u) r[u] = cmul(r[u], tw[u]);
     }
 
-    if constexpr (MODE == K_INV_ARGMAX) {
+    if constexpr (ARGMAX) {
         // pass 0 of the inverse: row m1, column j  ->  lag index m = m1*s + j (natural order).
         // rank = (m + lag_neg_max) mod L orders the lags like scipy's 'full' output; a lag is
         // searched iff rank <= lag_pos_max + lag_neg_max.
@@ -427,6 +474,152 @@ __global__ void __launch_bounds__(kThreads, min_ctas(LOGE)) k_col(const PassPara
         const long long rstride = (long long)NT << logS;
 #pragma unroll
         for (int u = 0; u < E; ++u) { *out = r[u]; out += rstride; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA helpers (sm_100a): 2-D tiled bulk-tensor loads completing on an mbarrier
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// outermost inverse pass + arg-max, persistent and TMA-fed
+// ---------------------------------------------------------------------------------------
+// Same arithmetic as k_col<..., K_INV_ARGMAX[_PRE]>, but each CTA loops over tiles and the n x G
+// tile (n rows of G*8 contiguous bytes, row stride s*8 bytes) is brought into shared memory by
+// 2-D TMA box loads instead of per-thread strided LDGs.  The load of tile t+1 is issued as soon
+// as the last exchange read of tile t is done, so it overlaps the final radix stage, the |c|^2
+// arg-max and the start of the next iteration -- and the LSU queue carries no bulk global loads
+// that would stall the other resident CTA's shared-memory exchanges.
+// tmap: FLOAT32 tensor {2*s, n_items*n}, box {2*G, min(n, 256)}, no swizzle.
+template <int LOGN, int LOGE, bool PRE>
+__global__ void __launch_bounds__(kThreads, argmax_tma_ctas(LOGE)) k_col_argmax_tma(const PassParams p, const __grid_constant__ CUtensorMap tmap,
+                                                               const unsigned n_tiles) {
+    using GEO = TileGeom<LOGN, LOGE, true>;
+    constexpr int E = GEO::E, NT = GEO::NT, G = GEO::G, LOGG = GEO::LOGG, N = GEO::N;
+    static_assert(GEO::NSTAGES >= 2, "needs an exchange buffer");
+    constexpr int BOX_ROWS = N < 256 ? N : 256;
+    constexpr uint32_t TILE_BYTES = (uint32_t)GEO::TILE * sizeof(float2);
+    extern __shared__ float2 smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar;
+    // 128-byte aligned TMA destination, kept in the shared address space (LDS/STS, not generic LD/ST)
+    float2* smem = smem_raw + (((128u - (smem_u32(smem_raw) & 127u)) & 127u) >> 3);
+
+    int g, i0;
+    GEO::thread_map(threadIdx.x, g, i0);
+    const int logS = p.logS;
+    const int logM = LOGN + logS;                          // == logL for the outermost pass
+    const int log_tpb = logS - LOGG;                       // tiles per item (log2)
+    const uint32_t lmask = (1u << p.logL) - 1u;
+
+    auto issue = [&](unsigned idx) {                       // one thread
+        const unsigned jt = idx & ((1u << log_tpb) - 1u);
+        const unsigned item = idx >> log_tpb;
+        mbar_expect_tx(&mbar, TILE_BYTES);
+#pragma unroll
+        for (int c = 0; c < N / BOX_ROWS; ++c)
+            tma_load_2d(smem + c * BOX_ROWS * G, &tmap, (int)(jt << (LOGG + 1)), (int)(item << LOGN) + c * BOX_ROWS, &mbar);
+    };
+
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned idx = blockIdx.x;
+    if (threadIdx.x == 0 && idx < n_tiles) issue(idx);
+    uint32_t parity = 0;
+
+    for (; idx < n_tiles; idx += gridDim.x) {
+        const unsigned jt = idx & ((1u << log_tpb) - 1u);
+        const long long item = idx >> log_tpb;
+        const unsigned j = (jt << LOGG) + g;               // column
+        const long long base = j;                          // element offset inside the item (row 0)
+
+        mbar_wait(&mbar, parity);
+        parity ^= 1u;
+        float2 r[E];
+#pragma unroll
+        for (int u = 0; u < E; ++u) r[u] = smem[((i0 + u * NT) << LOGG) + g];
+        const unsigned next = idx + gridDim.x;
+        __syncthreads();                                   // dense tile consumed; buffer becomes the exchange area
+
+        if constexpr (!PRE) {
+            float2 tw[E];
+            row_twiddles<E>(tw, j, (uint32_t)i0, (uint32_t)NT, logM, true, p.scale);
+#pragma unroll
+            for (int u = 0; u < E; ++u) r[u] = cmul(r[u], tw[u]);
+        }
+
+        fft_tile<GEO, true, false>(r, smem, g, i0, p.tabs, [&]() {
+            // every generic-proxy access to the buffer is ordered before the async-proxy refill
+            fence_proxy_async();
+            __syncthreads();
+            if (threadIdx.x == 0 && next < n_tiles) {
+                fence_proxy_async();
+                issue(next);
+            }
+        });
+
+        // rank = (m + lag_neg_max) mod L orders the lags like scipy's 'full' output (see k_col)
+        const uint32_t span = (uint32_t)p.lag_pos_max + (uint32_t)p.lag_neg_max;
+        const uint32_t rank0 = ((uint32_t)base + ((uint32_t)i0 << logS) + (uint32_t)p.lag_neg_max) & lmask;
+        const uint32_t rstep = (uint32_t)NT << logS;
+        float v[E];
+        float bv = -1.f;
+        const uint32_t col_rank0 = (j + (uint32_t)p.lag_neg_max) & lmask;
+        const uint32_t excl = lmask - span;
+        const uint32_t smask = (1u << logS) - 1u;
+        const uint32_t first_excl = span + 1u + ((col_rank0 - (span + 1u)) & smask);
+        const bool all_valid = excl == 0u || first_excl > lmask || first_excl < span + 1u;
+        if (all_valid) {
+#pragma unroll
+            for (int u = 0; u < E; ++u) { v[u] = cnorm2(r[u]); bv = fmaxf(bv, v[u]); }
+        } else {
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+                const uint32_t rank = (rank0 + (uint32_t)u * rstep) & lmask;
+                v[u] = rank <= span ? cnorm2(r[u]) : -1.f;
+                bv = fmaxf(bv, v[u]);
+            }
+        }
+        uint32_t brank;
+        block_argmax(bv, brank, [&](float target) {
+            uint32_t best = 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < E; ++u)
+                if (v[u] == target) best = min(best, (rank0 + (uint32_t)u * rstep) & lmask);
+            return best;
+        });
+        if (threadIdx.x == 0) {
+            Partial out;
+            out.val = bv;
+            out.rank = brank;
+            p.partials[(item << log_tpb) + jt] = out;
+        }
     }
 }
 

@@ -1,5 +1,8 @@
 // rmx_lib.cu — plan management, pass scheduling, small kernels and the C ABI (include/rmx.h).
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -114,7 +117,13 @@ static int choose_contig_loge(int logn) {
 
 static int choose_passes(rmx_plan* pl) {
     const int logL = pl->logL;
-    const int maxc = max_contig_logn(5), maxk = max_col_logn(5), minn = 4;
+    int maxc = max_contig_logn(5);
+    const int maxk = max_col_logn(5), minn = 4;
+    // Two-pass plans whose column pass still fits one tile with 4096-point rows use those: the 16-values-
+    // per-thread row kernel keeps 3 CTAs per SM and measured ~12 % faster per element than the 8192-point
+    // one (B200, L = 2^22), and the column pass of length 512/1024 takes the TMA-fed kernel.
+    if (logL - 12 >= 5 && logL - 12 <= maxk) maxc = 12;
+    { const char* e = getenv("RMX_CONTIG_LOGN"); if (e && atoi(e) >= 8 && atoi(e) <= max_contig_logn(5)) maxc = atoi(e); }   // developer override
     if (logL < minn) return fail(RMX_ERR_UNSUPPORTED, "fft_len 2^%d is below the minimum 2^%d", logL, minn);
     if (logL <= maxc) {
         pl->n_passes = 1;
@@ -226,6 +235,7 @@ static WindowMode window_mode(const rmx_plan* pl, int n_pairs) {
     else return w;
     if (!get_contig_kernel(pl->logn[last], pl->loge[last], mode).fn) return w;
     const int wu = window_wu(mode);
+    if (2LL * wu * nt * 2 > (1LL << pl->logn[last])) return w;   // window wider than half a row: nothing to prune
     const long long rows = 1LL << (pl->logL - pl->logn[last]);
     w.mode = mode;
     w.slots = 2 * wu * nt;
@@ -335,10 +345,91 @@ static PassParams base_params(const rmx_plan* pl) {
     return pp;
 }
 
+static bool twiddle_in_contig() {
+    static const bool v = getenv("RMX_TWIDDLE_IN_COL") == nullptr;
+    return v;
+}
+
+// The contiguous inverse pass (C_INV_PAIR) also applies the input twiddles -- and, for two-pass plans,
+// the 1/L -- of the column pass that runs next (pass n_passes-2); that pass is launched pre_twiddled.
+static void set_post_twiddle(const rmx_plan* pl, PassParams* pp) {
+    const int np = pl->n_passes;
+    if (np < 2 || !twiddle_in_contig()) return;
+    const int t = np - 2;
+    pp->post_logm = pl->logn[t] + pl->logs[t];
+    pp->post_logn = pl->logn[t];
+    pp->post_scale = t == 0 ? 1.0f / (float)(size_t(1) << pl->logL) : 1.0f;
+}
+
 static unsigned tiles_of(const rmx_plan* pl, int pass, long long n_items) {
     const int logtile = kLogThreads + pl->loge[pass];
     const long long total = n_items << pl->logL;
     return (unsigned)((total + (1LL << logtile) - 1) >> logtile);
+}
+
+
+// ---------------------------------------------------------------------------------------
+// TMA descriptors (cuTensorMapEncodeTiled resolved through the runtime; libcuda is not linked)
+// ---------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }();
+    return fn;
+}
+
+static int sm_count() {
+    static int n = []() {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v > 0 ? v : 148;
+    }();
+    return n;
+}
+
+// outermost inverse pass + arg-max through the persistent TMA-fed kernel; returns RMX_ERR_UNSUPPORTED
+// (without setting an error) when this plan / pointer cannot take that path
+static int launch_argmax_tma(const rmx_plan* pl, const PassParams& pp, bool pre, int cnt, cudaStream_t st, bool* taken) {
+    *taken = false;
+    if (getenv("RMX_NO_TMA")) return RMX_OK;
+    const TmaKernelEntry k = get_argmax_tma_kernel(pl->logn[0], pl->loge[0], pre);
+    auto enc = tensor_map_encoder();
+    if (!k.fn || !enc) return RMX_OK;
+    if (pl->logn[0] + pl->logs[0] != pl->logL) return RMX_OK;            // pass 0 spans the whole item
+    if ((reinterpret_cast<uintptr_t>(pp.src) & 15) != 0) return RMX_OK;
+    const unsigned long long s = 1ULL << pl->logs[0], n = 1ULL << pl->logn[0];
+    if (2 * s > (1ULL << 32) - 1 || (unsigned long long)cnt * n > (1ULL << 31) - 1) return RMX_OK;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {2 * s, (cuuint64_t)cnt * n};
+    const cuuint64_t gstride[1] = {s * sizeof(float2)};
+    const cuuint32_t box[2] = {(cuuint32_t)(2u << k.logG), (cuuint32_t)k.box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(pp.src), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RMX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    const unsigned n_tiles = tiles_of(pl, 0, cnt);
+    const unsigned grid = std::min<unsigned>(n_tiles, (unsigned)k.ctas_per_sm * (unsigned)sm_count());
+    CUDA_TRY(cudaFuncSetAttribute((const void*)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem_bytes));
+    {
+        ProfScope prof(pl, "col_inv_argmax", st);
+        k.fn<<<grid, kThreads, k.smem_bytes, st>>>(pp, tmap, n_tiles);
+    }
+    LAUNCH_CHECK("col_inv_argmax_tma");
+    *taken = true;
+    return RMX_OK;
+}
+
+// innermost inverse pass over `cnt` pairs
+static int launch_pair_pass(const rmx_plan* pl, const PassParams& pp, int cnt, cudaStream_t st) {
+    const int last = pl->n_passes - 1;
+    return launch_pass(pl, get_contig_kernel(pl->logn[last], pl->loge[last], C_INV_PAIR), "contig_inv_pair",
+                       dim3(tiles_of(pl, last, cnt)), pp, st);
 }
 
 // forward FFT of n_items signals from cu8 (optionally windowed) into `spectra`
@@ -436,7 +527,7 @@ __device__ __forceinline__ float parabolic(float ym, float y0, float yp) {
 // n_0-term sums over the input of the outermost inverse pass (still in the workspace).
 __global__ void __launch_bounds__(128) k_finalize_sum(const Partial* __restrict__ partials, int tiles_per_item,
                                                       const float2* __restrict__ D, int logL, int logn0, int logs0,
-                                                      int lag_pos_max, int lag_neg_max, float scale,
+                                                      int lag_pos_max, int lag_neg_max, float scale, int pre_twiddled,
                                                       rmx_peak* __restrict__ out) {
     __shared__ float s_v[4];
     __shared__ uint32_t s_l[4];
@@ -473,7 +564,8 @@ __global__ void __launch_bounds__(128) k_finalize_sum(const Partial* __restrict_
             const unsigned long long j = m & ((1ULL << logs0) - 1ULL);
             for (int k = threadIdx.x; k < n0; k += blockDim.x) {
                 const float2 v = Dp[((long long)k << logs0) + (long long)j];
-                const unsigned long long e = ((unsigned long long)k * m) & (unsigned long long)(L - 1);
+                // D[k][j] * w_L^{k*m}; a pre-twiddled workspace already carries w_L^{k*j}
+                const unsigned long long e = ((unsigned long long)k * (pre_twiddled ? m - j : m)) & (unsigned long long)(L - 1);
                 const float2 w = unit_root((uint32_t)e, logL, true);
                 const float2 t = cmul(v, w);
                 acc.x += t.x; acc.y += t.y;
@@ -663,14 +755,21 @@ extern "C" int rmx_xcorr_pairs_peak(const rmx_plan* pl, const rmx_complex64* spe
         pp.scale = np == 1 ? inv_len : 1.0f;
         // innermost pass first: rows of X_j * conj(X_i)
         pp.tabs = pl->tabs[np - 1];
-        int rc = launch_pass(pl, get_contig_kernel(pl->logn[np - 1], pl->loge[np - 1], C_INV_PAIR), "contig_inv_pair",
-                             dim3(tiles_of(pl, np - 1, cnt)), pp, st);
+        set_post_twiddle(pl, &pp);
+        int rc = launch_pair_pass(pl, pp, cnt, st);
         if (rc) return rc;
         for (int t = np - 2; t >= 0; --t) {
             pp.tabs = pl->tabs[t];
             pp.logS = pl->logs[t];
             pp.scale = t == 0 ? inv_len : 1.0f;
-            rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], t == 0 ? K_INV_ARGMAX : K_INV),
+            const bool pre = (t == np - 2) && twiddle_in_contig();      // twiddled by the contiguous pass
+            if (t == 0) {
+                bool taken = false;
+                rc = launch_argmax_tma(pl, pp, pre, cnt, st, &taken);
+                if (rc) return rc;
+                if (taken) continue;
+            }
+            rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], t == 0 ? (pre ? K_INV_ARGMAX_PRE : K_INV_ARGMAX) : (pre ? K_INV_PRE : K_INV)),
                              t == 0 ? "col_inv_argmax" : "col_inv", dim3(tiles_of(pl, t, cnt)), pp, st);
             if (rc) return rc;
         }
@@ -683,8 +782,11 @@ extern "C" int rmx_xcorr_pairs_peak(const rmx_plan* pl, const rmx_complex64* spe
         } else {
             {
                 ProfScope prof(pl, "finalize_sum", st);
+                // two-pass plans: the workspace (input of pass 0) is pre-twiddled and already scaled
                 k_finalize_sum<<<cnt, 128, 0, st>>>(partials, tpi, D, pl->logL, pl->logn[0], pl->logs[0],
-                                                    (int)pl->lag_pos_max, (int)pl->lag_neg_max, inv_len, out + first);
+                                                    (int)pl->lag_pos_max, (int)pl->lag_neg_max,
+                                                    (np == 2 && twiddle_in_contig()) ? 1.0f : inv_len,
+                                                    (np == 2 && twiddle_in_contig()) ? 1 : 0, out + first);
             }
             LAUNCH_CHECK("finalize_sum");
         }
@@ -708,13 +810,13 @@ extern "C" int rmx_xcorr_full(const rmx_plan* pl, const rmx_complex64* spectra, 
     const float inv_len = 1.0f / (float)(size_t(1) << pl->logL);
     pp.scale = np == 1 ? inv_len : 1.0f;
     pp.tabs = pl->tabs[np - 1];
-    int rc = launch_pass(pl, get_contig_kernel(pl->logn[np - 1], pl->loge[np - 1], C_INV_PAIR), "contig_inv_pair",
-                         dim3(tiles_of(pl, np - 1, n_pairs)), pp, st);
+    set_post_twiddle(pl, &pp);
+    int rc = launch_pair_pass(pl, pp, n_pairs, st);
     for (int t = np - 2; rc == RMX_OK && t >= 0; --t) {
         pp.tabs = pl->tabs[t];
         pp.logS = pl->logs[t];
         pp.scale = t == 0 ? inv_len : 1.0f;
-        rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], K_INV), "col_inv", dim3(tiles_of(pl, t, n_pairs)), pp, st);
+        rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], (t == np - 2 && twiddle_in_contig()) ? K_INV_PRE : K_INV), "col_inv", dim3(tiles_of(pl, t, n_pairs)), pp, st);
     }
     return rc;
 }
