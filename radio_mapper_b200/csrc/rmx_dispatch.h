@@ -23,6 +23,14 @@ struct TmaKernelEntry {
 // persistent TMA-fed arg-max pass (32 values per thread; n = 512 or 1024)
 TmaKernelEntry get_argmax_tma_kernel(int logn, int loge, bool pre_twiddled);
 
+// X_i-stationary pair pass (one row per tile, 16 values per thread: n = 4096); run = pairs per CTA
+struct PairRunEntry {
+    PassKernel fn;       // nullptr if not instantiated
+    size_t smem_bytes;
+    int run;
+};
+PairRunEntry get_pair_run_kernel(int logn, int loge);
+
 KernelEntry get_contig_kernel(int logn, int loge, int mode);
 KernelEntry get_col_kernel(int logn, int loge, int mode);
 

@@ -42,4 +42,15 @@ KernelEntry get_contig_kernel(int logn, int loge, int mode) {
     }
 }
 
+#ifndef RMX_PAIR_RUN
+#define RMX_PAIR_RUN 8
+#endif
+PairRunEntry get_pair_run_kernel(int logn, int loge) {
+    if (logn == 12 && loge == 4) {
+        using GEO = TileGeom<12, 4, false>;
+        return PairRunEntry{(PassKernel)k_contig_pair_run<12, 4, RMX_PAIR_RUN>, GEO::SMEM_BYTES, RMX_PAIR_RUN};
+    }
+    return PairRunEntry{nullptr, 0, 0};
+}
+
 }  // namespace rmx

@@ -22,6 +22,9 @@
 #ifndef RMX_PAIR_TWTREE
 #define RMX_PAIR_TWTREE 1   // contiguous pair pass: build stage twiddles from their power-of-two entries
 #endif
+#ifndef RMX_PAIR_RUN_CTAS
+#define RMX_PAIR_RUN_CTAS 3   // resident CTAs per SM for the X_i-stationary pair pass
+#endif
 #ifndef RMX_PAIR_CTAS
 #define RMX_PAIR_CTAS 2     // resident CTAs per SM requested for the contiguous pair pass (32 values/thread)
 #endif
@@ -474,6 +477,65 @@ __global__ void __launch_bounds__(kThreads, (MODE == K_INV_ARGMAX_PRE && LOGE ==
         const long long rstride = (long long)NT << logS;
 #pragma unroll
         for (int u = 0; u < E; ++u) { *out = r[u]; out += rstride; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// innermost inverse pass, X_i-stationary: one CTA walks RUN consecutive pairs of one row
+// ---------------------------------------------------------------------------------------
+// Same arithmetic as k_contig<..., C_INV_PAIR> for one row per tile (n == TILE).  Pair lists are
+// ordered by first buoy (i < j, i-major), so consecutive pairs share X_i: the CTA keeps the X_i row
+// in registers and re-reads it only when i changes.  That removes ~8*(1 - 1/RUN) of the 24 bytes
+// per element this pass moves through L2 and L1 (it is bound by exactly that traffic), and the
+// per-row twiddle powers are computed once per CTA instead of once per pair.
+template <int LOGN, int LOGE, int RUN>
+__global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run(const PassParams p) {
+    using GEO = TileGeom<LOGN, LOGE, false>;
+    constexpr int E = GEO::E, NT = GEO::NT;
+    static_assert(GEO::G == 1 && GEO::NSTAGES >= 2, "one row per tile");
+    extern __shared__ float2 smem[];
+    __shared__ float2 s_pw[8];
+
+    const int i0 = threadIdx.x, g = 0;
+    const unsigned n_blocks = ((unsigned)p.n_items + RUN - 1) / RUN;
+    const unsigned blk = blockIdx.x % n_blocks;              // pair-block fastest: CTAs that run together share rows
+    const long long row = blockIdx.x / n_blocks;
+    const uint32_t rr = (uint32_t)row & ((1u << p.post_logn) - 1u);
+    if (p.post_logm > 0 && threadIdx.x < LOGE) {
+        const uint32_t mask = (p.post_logm >= 32) ? 0xffffffffu : ((1u << p.post_logm) - 1u);
+        s_pw[threadIdx.x] = unit_root((rr * ((uint32_t)NT << threadIdx.x)) & mask, p.post_logm, true);
+    }
+    float2 a[E];
+    int cur_i = -1;
+    const int first = (int)blk * RUN;
+    const int last = min(first + RUN, p.n_items);
+    for (int pidx = first; pidx < last; ++pidx) {
+        const int2 pr = __ldg(p.pairs + pidx);
+        if (pr.x != cur_i) {                                  // CTA-uniform
+            const float2* __restrict__ xi = p.spectra + ((long long)pr.x << p.logL) + (row << LOGN);
+#pragma unroll
+            for (int u = 0; u < E; ++u) a[u] = __ldg(xi + i0 + u * NT);
+            cur_i = pr.x;
+        }
+        const float2* __restrict__ xj = p.spectra + ((long long)pr.y << p.logL) + (row << LOGN);
+        float2 r[E];
+#pragma unroll
+        for (int u = 0; u < E; ++u) r[u] = cmul_conj(__ldg(xj + i0 + u * NT), a[u]);     // X_j * conj(X_i)
+        if (pidx != first) __syncthreads();                  // previous pair's last exchange read is done
+        fft_tile<GEO, true, (RMX_PAIR_TWTREE != 0)>(r, smem, g, i0, p.tabs);
+        if (p.post_logm > 0) {
+            float2 tw[E];
+            row_twiddles_shared<E>(tw, rr, (uint32_t)i0, p.post_logm, true, p.post_scale, s_pw);
+#pragma unroll
+            for (int u = 0; u < E; ++u) r[u] = cmul(r[u], tw[u]);
+        }
+        if (p.scale != 1.0f) {
+#pragma unroll
+            for (int u = 0; u < E; ++u) { r[u].x *= p.scale; r[u].y *= p.scale; }
+        }
+        float2* __restrict__ out = p.dst + (long long)pidx * p.src_item_stride + (row << LOGN);
+#pragma unroll
+        for (int u = 0; u < E; ++u) out[i0 + u * NT] = r[u];
     }
 }
 

@@ -428,6 +428,12 @@ static int launch_argmax_tma(const rmx_plan* pl, const PassParams& pp, bool pre,
 // innermost inverse pass over `cnt` pairs
 static int launch_pair_pass(const rmx_plan* pl, const PassParams& pp, int cnt, cudaStream_t st) {
     const int last = pl->n_passes - 1;
+    const PairRunEntry kr = get_pair_run_kernel(pl->logn[last], pl->loge[last]);
+    if (kr.fn && pl->n_passes >= 2 && !getenv("RMX_NO_PAIR_RUN")) {
+        const long long rows = 1LL << (pl->logL - pl->logn[last]);
+        const long long blocks = (cnt + kr.run - 1) / kr.run;
+        return launch_pass(pl, KernelEntry{kr.fn, kr.smem_bytes, 0}, "contig_inv_pair", dim3((unsigned)(rows * blocks)), pp, st);
+    }
     return launch_pass(pl, get_contig_kernel(pl->logn[last], pl->loge[last], C_INV_PAIR), "contig_inv_pair",
                        dim3(tiles_of(pl, last, cnt)), pp, st);
 }
