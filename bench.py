@@ -48,6 +48,19 @@ def algorithmic_bytes(B, P, N, L):
     return B * (2 * N + 8 * L) + P * (16 * L + 16), B * (2 * N + 8 * L), P * (16 * L + 16)
 
 
+def measured_traffic(workload, B, P, L):
+    """DRAM bytes per launch of the correlate+peak stage, scaled from the ncu --set full capture recorded in
+    profiles/r01_traffic.json (per-unit ratios measured on the same kernels at the same FFT length)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)[workload]
+        unit = 8 * L
+        return int(unit * (B * t["pair_pass_read_per_buoy_unit8L"] + P * (t["pair_pass_write_per_pair_unit8L"] +
+                                                                          t["argmax_pass_read_per_pair_unit8L"]))), t["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -314,10 +327,11 @@ def run_b200(args, wl):
     n_calls = args.steps * W                               # one correlate call per window
     pair_gbs = pair_b * n_calls / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else 0.0
     whole_gbs = total_b * W * args.steps / (elapsed_ms * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(args.workload, B, P, L)
     roofline = {
         "bound": "hbm", "kernel": "correlate+peak stage (" + " + ".join(sorted(pair_names)) + ")",
-        "achieved": pair_gbs, "peak": peak, "unit": "GB/s", "frac": pair_gbs / peak, "traffic": None,
-        "peak_source": peak_src, "algorithmic_bytes_per_launch": pair_b,
+        "achieved": pair_gbs, "peak": peak, "unit": "GB/s", "frac": pair_gbs / peak, "traffic": traffic,
+        "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": pair_b,
         "avg_launch_ms": pair_ms / max(1, n_calls), "share_of_step": pair_ms / max(1e-9, pair_ms + fwd_ms),
         "whole_step": {"achieved": whole_gbs, "frac": whole_gbs / peak, "algorithmic_bytes_per_window": total_b},
         "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items())},
