@@ -184,6 +184,39 @@ def test_xcorr_one_pass_windowed_search(rmx, log_n, max_lag):
         plan.set_search_mode(False)
 
 
+@pytest.mark.parametrize("log_n", [17, 20, 22])
+def test_kernel_variants_agree(rmx, monkeypatch, log_n):
+    """The TMA-fed arg-max pass, the X_i-stationary row pass and the twiddle placement are
+    re-arrangements of the same arithmetic: every variant must return the oracle's lags, and peaks /
+    sub-sample offsets inside the north_star tolerances of each other (plans 32x4096, 256x4096, 1024x8192)."""
+    n = 1 << log_n
+    iq, delays, _ = synth.delayed_buoys(1200 + log_n, 5, n, max_delay=300)
+    want = np.array([delays[j] - delays[i] for i, j in oracle.pair_list(5)])
+    pairs = _cuda(rmx.pair_table(5))
+    results = {}
+    for name, env in [("default", {}), ("no_tma", {"RMX_NO_TMA": "1"}), ("no_pair_run", {"RMX_NO_PAIR_RUN": "1"}),
+                      ("twiddle_in_col", {"RMX_TWIDDLE_IN_COL": "1"}),
+                      ("all_off", {"RMX_NO_TMA": "1", "RMX_NO_PAIR_RUN": "1", "RMX_TWIDDLE_IN_COL": "1"})]:
+        for k in ("RMX_NO_TMA", "RMX_NO_PAIR_RUN", "RMX_TWIDDLE_IN_COL"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        plan = rmx.Plan(5, n)
+        S = plan.forward(_cuda(iq))
+        results[name] = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, pairs)).copy()
+        full = plan.xcorr_full(S, pairs[:2].contiguous()).cpu().numpy()
+        results[name + "_full"] = full
+    ref = results["default"]
+    assert np.array_equal(ref["lag"], want)
+    for name in ("no_tma", "no_pair_run", "twiddle_in_col", "all_off"):
+        _check_records(results[name], ref)
+        a, b = results[name + "_full"], results["default_full"]
+        assert np.linalg.norm(a - b) <= 2e-6 * np.linalg.norm(b), name
+    # same arithmetic, different data movement: bit-identical records
+    assert results["no_tma"].tobytes() == ref.tobytes()
+    assert results["no_pair_run"].tobytes() == ref.tobytes()
+
+
 def test_xcorr_edge_inputs(rmx):
     """Saturated / constant inputs and peaks on the edge of the lag range."""
     n = 4096
