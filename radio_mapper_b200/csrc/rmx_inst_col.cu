@@ -38,4 +38,22 @@ KernelEntry get_col_kernel(int logn, int loge, int mode) {
     }
 }
 
+// TMA-fed arg-max pass with 16 values per thread: n = 64, 128, 256 (two-stage transforms whose
+// G = 4096/n columns make 512 / 256 / 128-byte rows)
+template <int LOGN, bool PRE>
+static TmaKernelEntry tma_entry16() {
+    using GEO = TileGeom<LOGN, 4, true>;
+    return TmaKernelEntry{(ArgmaxTmaKernel)k_col_argmax_tma<LOGN, 4, PRE>, GEO::SMEM_BYTES + 128, GEO::LOGG,
+                          GEO::N < 256 ? GEO::N : 256, argmax_tma_ctas(4)};
+}
+
+TmaKernelEntry get_argmax_tma_kernel16(int logn, bool pre) {
+    switch (logn) {
+        case 6: return pre ? tma_entry16<6, true>() : tma_entry16<6, false>();
+        case 7: return pre ? tma_entry16<7, true>() : tma_entry16<7, false>();
+        case 8: return pre ? tma_entry16<8, true>() : tma_entry16<8, false>();
+        default: return TmaKernelEntry{nullptr, 0, 0, 0, 0};
+    }
+}
+
 }  // namespace rmx

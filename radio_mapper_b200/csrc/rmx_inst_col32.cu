@@ -38,9 +38,12 @@ static TmaKernelEntry tma_entry() {
                           GEO::N < 256 ? GEO::N : 256, argmax_tma_ctas(5)};
 }
 
+TmaKernelEntry get_argmax_tma_kernel16(int logn, bool pre);   // rmx_inst_col.cu
+
 TmaKernelEntry get_argmax_tma_kernel(int logn, int loge, bool pre) {
     if (loge == 5 && logn == 10) return pre ? tma_entry<10, true>() : tma_entry<10, false>();
     if (loge == 5 && logn == 9) return pre ? tma_entry<9, true>() : tma_entry<9, false>();
+    if (loge == 4) return get_argmax_tma_kernel16(logn, pre);
     return TmaKernelEntry{nullptr, 0, 0, 0, 0};
 }
 

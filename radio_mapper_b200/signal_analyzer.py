@@ -173,7 +173,7 @@ class SignalAnalyzer:
         return dict(power_db=db, frequencies_mhz=freqs, blocks=out)
 
     def welch_detect(self, iq_u8, sample_rate, center_freq_mhz, nperseg: int = 65536, threshold_db: float = 10.0,
-                     segments_in_flight: int = 256):
+                     segments_in_flight: Optional[int] = None):
         """Welch PSD (Hann, no overlap, density scaling == scipy.signal.welch) of a cu8 stream
         and threshold detection over the frequency bins: bins that are local maxima of the dB
         spectrum and exceed mean + threshold_db.  iq_u8: uint8[2*W*nperseg] (host or device).
