@@ -136,7 +136,11 @@ RMX_API int rmx_spectrum_db(const rmx_plan* plan, const rmx_complex64* spectra, 
 
 /* Stage 5b — Welch PSD (Hann, no overlap, no detrend, two-sided, density scaling): the plan's
  * n_signals are the segments, n_samples == fft_len == nperseg.  psd: float[fft_len], natural order.
- * == scipy.signal.welch(x, fs, 'hann', nperseg, 0, detrend=False, return_onesided=False) */
+ * == scipy.signal.welch(x, fs, 'hann', nperseg, 0, detrend=False, return_onesided=False)
+ * nperseg = 16384 / 32768 / 65536 (and iq 8-byte aligned) runs as ONE kernel on thread-block clusters of
+ * 2 / 4 / 8 CTAs that hold each segment in distributed shared memory; it touches only the first
+ * 4*fft_len bytes of the workspace.  Other sizes take two passes through a spectra workspace of
+ * 8*fft_len bytes per segment in flight. */
 RMX_API int rmx_welch_psd(rmx_plan* plan, const uint8_t* iq, float* psd, double sample_rate,
                   void* workspace, size_t workspace_bytes, void* stream);
 RMX_API size_t rmx_welch_workspace_bytes(const rmx_plan* plan, int segments_in_flight);

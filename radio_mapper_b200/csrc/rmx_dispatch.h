@@ -31,6 +31,15 @@ struct PairRunEntry {
 };
 PairRunEntry get_pair_run_kernel(int logn, int loge);
 
+typedef void (*WelchClusterKernel)(const WelchClusterParams);
+struct WelchClusterEntry {
+    WelchClusterKernel fn;   // nullptr unless log2(cluster size) is 1, 2 or 3
+    size_t smem_bytes;
+    int cluster;
+};
+// one-kernel Welch PSD for nperseg = cluster * 8192
+WelchClusterEntry get_welch_cluster_kernel(int logc);
+
 KernelEntry get_contig_kernel(int logn, int loge, int mode);
 KernelEntry get_col_kernel(int logn, int loge, int mode);
 

@@ -568,6 +568,108 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
 }
 
 // ---------------------------------------------------------------------------------------
+// Welch PSD, one kernel: a thread-block cluster holds a whole segment on chip
+// ---------------------------------------------------------------------------------------
+// nperseg = C * n (C = 2, 4 or 8 CTAs per cluster; n = 8192 points per CTA).  The two passes of
+// the forward transform (column FFTs of length C at stride n, twiddle, row FFTs of length n) run
+// back to back inside the cluster: CTA c computes the length-C column transforms of its n/C
+// columns straight from cu8 (unpack, Hann window), multiplies by w_L^{j*k} and scatters output
+// row k to CTA k through distributed shared memory; after a cluster barrier every CTA owns one
+// complete row, transforms it and accumulates |X|^2 in registers across the segments its cluster
+// walks.  The 8*nperseg-byte spectrum never goes to HBM (the two-pass path writes and re-reads it).
+// Layout of `accum`: position k*n + m holds bin k + C*m (digit-transposed, passes {C, n}).
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_id_x() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_count_x() { unsigned r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_cluster_f2(uint32_t local_addr, unsigned rank, float2 v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(v.x), "f"(v.y) : "memory");
+}
+
+struct WelchClusterParams {
+    const uint8_t* cu8;       // [n_segments][2*nperseg]
+    const float* window;      // [nperseg]
+    float* accum;             // [nperseg], zeroed by the caller
+    StageTables tabs;         // stage tables of the n-point row transform (32 values per thread)
+    int n_segments;
+    int logL;                 // log2(nperseg)
+};
+
+template <int LOGC>
+__global__ void __launch_bounds__(kThreads, 2) k_welch_cluster(const WelchClusterParams p) {
+    using GEO = TileGeom<13, 5, false>;
+    constexpr int E = GEO::E, NT = GEO::NT, N = GEO::N, C = 1 << LOGC;
+    constexpr int CPT = E / C;                               // columns per thread in the column phase
+    extern __shared__ float2 smem[];
+    const unsigned c = cluster_ctarank();
+    const int t = threadIdx.x, i0 = threadIdx.x, g = 0;
+    const uint32_t lmask = (1u << p.logL) - 1u;
+    const uint32_t smem_base = smem_u32(smem);
+
+    float acc[E];
+#pragma unroll
+    for (int u = 0; u < E; ++u) acc[u] = 0.f;
+
+    bool first = true;
+    for (int seg = (int)cluster_id_x(); seg < p.n_segments; seg += (int)cluster_count_x()) {
+        const uint8_t* __restrict__ in = p.cu8 + ((size_t)seg << (p.logL + 1));
+        // ---- column phase: CPT columns x C rows per thread --------------------------------------
+        // (columns t + 256*v: 8-byte lanes of a warp are contiguous in the destination row, which is what
+        // the distributed-shared-memory stores want; 16-byte stores of adjacent columns measured 1.45x slower)
+        float2 y[CPT][C];
+#pragma unroll
+        for (int v = 0; v < CPT; ++v) {
+            const uint32_t j = c * (uint32_t)(N / C) + (uint32_t)t + 256u * v;
+#pragma unroll
+            for (int r = 0; r < C; ++r) {
+                const uint32_t n = (uint32_t)r * N + j;
+                const uchar2 b = *reinterpret_cast<const uchar2*>(in + 2 * (size_t)n);
+                const float w = __ldg(p.window + n);
+                y[v][r] = make_float2(((float)b.x - 127.5f) * w, ((float)b.y - 127.5f) * w);
+            }
+            dft_regs<C, false>(y[v]);
+            // twiddle w_L^{-j*k}, k = 1..C-1: exact base root, powers by a product tree
+            float2 pw[C];
+            pw[1] = unit_root(j & lmask, p.logL, false);
+            static_for<2, C>([&](auto K_) {
+                constexpr int k = decltype(K_)::value;
+                pw[k] = cmul(pw[k / 2], pw[k - k / 2]);
+            });
+            static_for<1, C>([&](auto K_) {
+                constexpr int k = decltype(K_)::value;
+                y[v][k] = cmul(y[v][k], pw[k]);
+            });
+        }
+        if (!first) cluster_wait();                          // every CTA of the cluster is done with its row buffer
+        first = false;
+#pragma unroll
+        for (int v = 0; v < CPT; ++v) {
+            const uint32_t j = c * (uint32_t)(N / C) + (uint32_t)t + 256u * v;
+#pragma unroll
+            for (int k = 0; k < C; ++k) st_cluster_f2(smem_base + j * (uint32_t)sizeof(float2), (unsigned)k, y[v][k]);
+        }
+        cluster_arrive();
+        cluster_wait();                                      // all rows are complete
+        // ---- row phase: this CTA's row k = c ------------------------------------------------------
+        float2 r[E];
+#pragma unroll
+        for (int u = 0; u < E; ++u) r[u] = smem[i0 + u * NT];
+        __syncthreads();                                     // dense row consumed; buffer becomes the exchange area
+        fft_tile<GEO, false>(r, smem, g, i0, p.tabs);
+#pragma unroll
+        for (int u = 0; u < E; ++u) acc[u] += cnorm2(r[u]);
+        cluster_arrive();                                    // my reads of the buffer are done (matched at the top)
+    }
+    if (!first) cluster_wait();
+    float* __restrict__ out = p.accum + (size_t)c * N;
+#pragma unroll
+    for (int u = 0; u < E; ++u) atomicAdd(out + i0 + u * NT, acc[u]);
+}
+
+// ---------------------------------------------------------------------------------------
 // outermost inverse pass + arg-max, persistent and TMA-fed
 // ---------------------------------------------------------------------------------------
 // Same arithmetic as k_col<..., K_INV_ARGMAX[_PRE]>, but each CTA loops over tiles and the n x G

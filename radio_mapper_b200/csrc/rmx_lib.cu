@@ -72,6 +72,8 @@ struct rmx_plan {
     double hann_sumsq = 0.0;
     long long lag_pos_max = 0, lag_neg_max = 0;
     bool force_full_search = false;   // true: never take the one-pass windowed path
+    StageTables welch_row_tabs;       // 8192-point row transform of the cluster Welch kernel (built on first use)
+    bool welch_row_tabs_ready = false;
 };
 
 static int build_stage_tables(rmx_plan* pl, int logn, int loge, StageTables* out) {
@@ -1080,6 +1082,63 @@ extern "C" int rmx_welch_psd(rmx_plan* pl, const uint8_t* iq, float* psd, double
         return fail(RMX_ERR_WORKSPACE, "Welch workspace too small: %zu bytes", workspace_bytes);
     float* accum = reinterpret_cast<float*>(workspace);
     float2* Y = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) + accum_bytes);
+    {
+        // one-kernel path: nperseg = C * 8192 with a cluster of C = 2, 4 or 8 CTAs holding the segment on chip
+        const WelchClusterEntry k = get_welch_cluster_kernel(pl->logL - 13);
+        if (k.fn && !getenv("RMX_NO_WELCH_CLUSTER") && (reinterpret_cast<uintptr_t>(iq) & 7) == 0) {
+            if (!pl->welch_row_tabs_ready) {
+                rc = build_stage_tables(pl, 13, 5, &pl->welch_row_tabs);
+                if (rc) return rc;
+                pl->welch_row_tabs_ready = true;
+            }
+            CUDA_TRY(cudaMemsetAsync(accum, 0, L * sizeof(float), st));
+            WelchClusterParams wp;
+            wp.cu8 = iq;
+            wp.window = pl->d_hann;
+            wp.accum = accum;
+            wp.tabs = pl->welch_row_tabs;
+            wp.n_segments = pl->n_signals;
+            wp.logL = pl->logL;
+            CUDA_TRY(cudaFuncSetAttribute((const void*)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem_bytes));
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)k.cluster);
+            cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = k.smem_bytes;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)k.cluster;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            // persistent clusters: exactly as many as can be resident at once (clusters are placed inside
+            // one GPC, so this is fewer than CTAs-per-SM * SMs / cluster size)
+            int max_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void*)k.fn, &cfg) != cudaSuccess || max_clusters < 1) {
+                cudaGetLastError();
+                max_clusters = std::max(1, sm_count() / k.cluster);
+            }
+            { const char* e = getenv("RMX_WELCH_CLUSTERS"); if (e && atoi(e) > 0) max_clusters = atoi(e); }
+            const int n_clusters = std::min(pl->n_signals, max_clusters);
+            cfg.gridDim = dim3((unsigned)(n_clusters * k.cluster));
+            {
+                ProfScope prof(pl, "welch_cluster", st);
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, k.fn, wp));
+            }
+            LAUNCH_CHECK("welch_cluster");
+            LayoutDesc d;
+            memset(&d, 0, sizeof(d));
+            d.n_passes = 2;
+            d.logn[0] = pl->logL - 13; d.logs[0] = 13;
+            d.logn[1] = 13; d.logs[1] = 0;
+            const float scale = (float)(1.0 / (sample_rate * pl->hann_sumsq * (double)pl->n_signals));
+            k_psd_finalize<<<grid_for((long long)L, 256), 256, 0, st>>>(d, accum, psd, pl->logL, scale);
+            LAUNCH_CHECK("psd_finalize");
+            return RMX_OK;
+        }
+    }
     const int group = (int)std::min<size_t>((size_t)pl->n_signals, (workspace_bytes - accum_bytes) / (L * sizeof(float2)));
     CUDA_TRY(cudaMemsetAsync(accum, 0, L * sizeof(float), st));
     const int np = pl->n_passes;

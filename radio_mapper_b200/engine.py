@@ -6,6 +6,7 @@ Every numeric stage runs in librmx.so through the C ABI of include/rmx.h.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -228,7 +229,10 @@ class Plan:
         segments per launch as fit 1 GiB -- fewer, larger launches measured faster on B200 (1000 x 64k bins:
         0.36 ms with all segments in flight, 0.45 ms with 256, 0.69 ms with 64)."""
         if segments_in_flight is None:
-            segments_in_flight = max(1, (1 << 30) // (8 * self.fft_len))
+            # nperseg = 2/4/8 * 8192 runs as one thread-block-cluster kernel that keeps each segment in
+            # distributed shared memory and needs no spectra workspace at all
+            single_kernel = self.fft_len in (1 << 14, 1 << 15, 1 << 16) and not os.environ.get("RMX_NO_WELCH_CLUSTER")
+            segments_in_flight = 1 if single_kernel else max(1, (1 << 30) // (8 * self.fft_len))
         _require_cuda(iq_u8, torch.uint8, "iq_u8")
         if self.n_samples != self.fft_len:
             raise ValueError("Welch plans need n_samples == fft_len")

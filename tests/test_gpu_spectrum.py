@@ -88,7 +88,7 @@ def test_signal_stats_parity(rmx):
     assert abs(mp2 / mp - 1) < 1e-6 and pk2 == pk
 
 
-@pytest.mark.parametrize("nperseg,n_seg", [(4096, 8), (8192, 5), (65536, 12), (65536, 70)])
+@pytest.mark.parametrize("nperseg,n_seg", [(4096, 8), (8192, 5), (16384, 9), (32768, 7), (65536, 12), (65536, 70)])
 def test_welch_parity(rmx, nperseg, n_seg):
     iq, bins = synth.welch_stream(3, n_seg, nperseg)
     plan = rmx.Plan(n_seg, nperseg, nperseg)
@@ -97,6 +97,21 @@ def test_welch_parity(rmx, nperseg, n_seg):
     assert np.max(np.abs(psd / ref - 1)) < 2e-5
     db = rmx.power_db(_cuda(psd)).cpu().numpy()
     assert np.max(np.abs(db - oracle.welch_db(ref))) < 1e-3
+
+
+@pytest.mark.parametrize("nperseg", [16384, 32768, 65536])
+def test_welch_cluster_kernel_matches_two_pass(rmx, monkeypatch, nperseg):
+    """nperseg = C*8192 runs as ONE kernel on a cluster of C CTAs (segment held in distributed shared
+    memory); RMX_NO_WELCH_CLUSTER=1 takes the two-pass path through HBM.  Same transform, different
+    factorisation: the PSDs agree to float32 rounding."""
+    n_seg = 45
+    iq, _ = synth.welch_stream(11, n_seg, nperseg)
+    plan = rmx.Plan(n_seg, nperseg, nperseg)
+    monkeypatch.delenv("RMX_NO_WELCH_CLUSTER", raising=False)
+    a = plan.welch_psd(_cuda(iq), 2.4e6).cpu().numpy()
+    monkeypatch.setenv("RMX_NO_WELCH_CLUSTER", "1")
+    b = plan.welch_psd(_cuda(iq), 2.4e6).cpu().numpy()
+    assert np.max(np.abs(a / b - 1)) < 2e-5
 
 
 def test_welch_detect_finds_the_tones(rmx):
