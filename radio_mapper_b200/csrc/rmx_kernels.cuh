@@ -19,6 +19,19 @@
 #include <cuda.h>   // CUtensorMap (type only; the driver entry point is resolved at run time)
 #include "rmx_fft_core.cuh"
 
+#ifndef RMX_X_LOAD
+#define RMX_X_LOAD __ldg      // spectrum loads of the pair passes (experiment: __ldcg / __ldcs / __ldlu)
+#endif
+#ifndef RMX_D_STORE_MODE
+#define RMX_D_STORE_MODE 0    // workspace stores of the pair passes: 0 plain, 1 __stcs (streaming), 2 __stcg
+#endif
+#if RMX_D_STORE_MODE == 1
+#define RMX_D_STORE(ptr, v) __stcs((ptr), (v))
+#elif RMX_D_STORE_MODE == 2
+#define RMX_D_STORE(ptr, v) __stcg((ptr), (v))
+#else
+#define RMX_D_STORE(ptr, v) (*(ptr) = (v))
+#endif
 #ifndef RMX_PAIR_TWTREE
 #define RMX_PAIR_TWTREE 1   // contiguous pair pass: build stage twiddles from their power-of-two entries
 #endif
@@ -286,7 +299,7 @@ k_contig(const PassParams p) {
 #pragma unroll
             for (int u = 0; u < E; ++u) {
                 if (active) {
-                    const float2 a = __ldg(xi + i0 + u * NT), b = __ldg(xj + i0 + u * NT);
+                    const float2 a = RMX_X_LOAD(xi + i0 + u * NT), b = RMX_X_LOAD(xj + i0 + u * NT);
                     r[u] = cmul_conj(b, a);                        // X_j * conj(X_i)
                 } else {
                     r[u] = make_float2(0.f, 0.f);
@@ -322,7 +335,10 @@ k_contig(const PassParams p) {
         if (active) {
             float2* __restrict__ out = p.dst + item * p.src_item_stride + (row << LOGN);
 #pragma unroll
-            for (int u = 0; u < E; ++u) out[i0 + u * NT] = r[u];
+            for (int u = 0; u < E; ++u) {
+                if constexpr (MODE == C_INV_PAIR) RMX_D_STORE(out + i0 + u * NT, r[u]);
+                else out[i0 + u * NT] = r[u];
+            }
         }
     }
 }
@@ -514,13 +530,13 @@ __global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run
         if (pr.x != cur_i) {                                  // CTA-uniform
             const float2* __restrict__ xi = p.spectra + ((long long)pr.x << p.logL) + (row << LOGN);
 #pragma unroll
-            for (int u = 0; u < E; ++u) a[u] = __ldg(xi + i0 + u * NT);
+            for (int u = 0; u < E; ++u) a[u] = RMX_X_LOAD(xi + i0 + u * NT);
             cur_i = pr.x;
         }
         const float2* __restrict__ xj = p.spectra + ((long long)pr.y << p.logL) + (row << LOGN);
         float2 r[E];
 #pragma unroll
-        for (int u = 0; u < E; ++u) r[u] = cmul_conj(__ldg(xj + i0 + u * NT), a[u]);     // X_j * conj(X_i)
+        for (int u = 0; u < E; ++u) r[u] = cmul_conj(RMX_X_LOAD(xj + i0 + u * NT), a[u]);     // X_j * conj(X_i)
         if (pidx != first) __syncthreads();                  // previous pair's last exchange read is done
         fft_tile<GEO, true, (RMX_PAIR_TWTREE != 0)>(r, smem, g, i0, p.tabs);
         if (p.post_logm > 0) {
@@ -535,7 +551,7 @@ __global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run
         }
         float2* __restrict__ out = p.dst + (long long)pidx * p.src_item_stride + (row << LOGN);
 #pragma unroll
-        for (int u = 0; u < E; ++u) out[i0 + u * NT] = r[u];
+        for (int u = 0; u < E; ++u) RMX_D_STORE(out + i0 + u * NT, r[u]);
     }
 }
 

@@ -420,6 +420,29 @@ class TDoAProcessor:
                 self.buoy_positions))
         return out
 
+    def correlate_stream(self, source, buoy_ids: Sequence[str], sample_rate: float = 2048000,
+                         frequency_mhz: float = 0.0, max_lag: Optional[int] = None, device=None, depth: int = 3,
+                         max_windows: Optional[int] = None):
+        """Streaming form of `correlate_iq`: `source` is an `ingest.Cu8FileSource` (one raw rtl_sdr capture
+        per buoy, `sdr_capture.py:26`), `ingest.Cu8PipeSource` (live `rtl_sdr ... -` pipes,
+        `iq_stream_client.py:101-116`) or `ingest.ArraySource`.  Windows go through a pinned host ring and
+        are copied to the GPU while the previous window is being correlated.  Yields, per window, the
+        list of `TDoAMeasurement`s `correlate_iq` would return for it."""
+        from . import ingest
+        from .engine import pair_table
+        if len(buoy_ids) != source.n_buoys:
+            raise ValueError("buoy_ids has %d entries but the source delivers %d buoys" % (len(buoy_ids), source.n_buoys))
+        cor = self._correlator(source.n_buoys, source.samples_per_window, device)
+        key = ("stream", id(cor), int(depth))
+        sc = self._correlators.get(key)
+        if sc is None:
+            sc = self._correlators[key] = ingest.StreamingCorrelator(cor, depth=depth)
+        pairs = pair_table(source.n_buoys)
+        for rec in sc.run(source, max_lag=max_lag, max_windows=max_windows):
+            yield self.tdoa_calculator.measurements_from_lags(
+                buoy_ids, pairs, rec["lag"], rec["frac"], rec["coherence"], sample_rate, frequency_mhz,
+                self.buoy_positions)
+
     def triangulate_iq(self, iq_u8, buoy_ids: Sequence[str], sample_rate: float = 2048000,
                        frequency_mhz: float = 0.0, signal_type: str = "unknown",
                        max_lag: Optional[int] = None, robust: bool = False) -> List[Optional[TriangulationResult]]:
