@@ -48,10 +48,13 @@ static TmaKernelEntry tma_entry16() {
 }
 
 TmaKernelEntry get_argmax_tma_kernel16(int logn, bool pre) {
+    // pre-twiddled input only (two-pass plans): with its own twiddle array the kernel no longer fits the
+    // 64 registers of 4 CTAs per SM and measured slower than the strided-load kernel (cfg5, n = 128)
+    if (!pre) return TmaKernelEntry{nullptr, 0, 0, 0, 0};
     switch (logn) {
-        case 6: return pre ? tma_entry16<6, true>() : tma_entry16<6, false>();
-        case 7: return pre ? tma_entry16<7, true>() : tma_entry16<7, false>();
-        case 8: return pre ? tma_entry16<8, true>() : tma_entry16<8, false>();
+        case 6: return tma_entry16<6, true>();
+        case 7: return tma_entry16<7, true>();
+        case 8: return tma_entry16<8, true>();
         default: return TmaKernelEntry{nullptr, 0, 0, 0, 0};
     }
 }

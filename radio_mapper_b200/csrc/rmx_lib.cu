@@ -125,6 +125,7 @@ static int choose_passes(rmx_plan* pl) {
     // per-thread row kernel keeps 3 CTAs per SM and measured ~12 % faster per element than the 8192-point
     // one (B200, L = 2^22), and the column pass of length 512/1024 takes the TMA-fed kernel.
     if (logL - 12 >= 5 && logL - 12 <= maxk) maxc = 12;
+    if (logL - 13 > maxk) maxc = 12;        // three passes: the 4096-point row kernels are ~15 % faster per element (cfg5)
     { const char* e = getenv("RMX_CONTIG_LOGN"); if (e && atoi(e) >= 8 && atoi(e) <= max_contig_logn(5)) maxc = atoi(e); }   // developer override
     if (logL < minn) return fail(RMX_ERR_UNSUPPORTED, "fft_len 2^%d is below the minimum 2^%d", logL, minn);
     if (logL <= maxc) {
