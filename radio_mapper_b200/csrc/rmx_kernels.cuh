@@ -32,6 +32,15 @@
 #else
 #define RMX_D_STORE(ptr, v) (*(ptr) = (v))
 #endif
+#ifndef RMX_PAIR_RUN_BULK_STORE
+#define RMX_PAIR_RUN_BULK_STORE 0   // same for the X_i-stationary 4096-point pass: measured 2-3 % slower (3 CTAs/SM hide the stores)
+#endif
+#ifndef RMX_FWD_BULK_STORE
+#define RMX_FWD_BULK_STORE 0    // forward row pass (C_FWD): measured 2 % slower with the bulk store
+#endif
+#ifndef RMX_PAIR_BULK_STORE
+#define RMX_PAIR_BULK_STORE 1   // row pass output through shared memory + cp.async.bulk (one row per tile)
+#endif
 #ifndef RMX_PAIR_TWTREE
 #define RMX_PAIR_TWTREE 1   // contiguous pair pass: build stage twiddles from their power-of-two entries
 #endif
@@ -107,6 +116,16 @@ __device__ __forceinline__ uint32_t row_frequency(const PassParams& p, uint32_t 
 }
 // *_PRE: the input already carries this pass's twiddles and scale (applied by the contiguous pass)
 enum ColMode { K_FWD_CU8 = 0, K_FWD = 1, K_INV = 2, K_INV_ARGMAX = 3, K_INV_PRE = 4, K_INV_ARGMAX_PRE = 5 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// shared -> global bulk copy (TMA engine); the issuing thread must wait for the read of shared memory
+// (bulk_store_wait_read) before the buffer is reused or the CTA exits
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 __device__ __forceinline__ float2 load_cu8_sample(const uint8_t* base, long long idx) {
     // (float)u8 - 127.5f, I then Q: exactly the reference's unpack (buoy_node.py:392-398)
@@ -332,7 +351,21 @@ k_contig(const PassParams p) {
                 for (int u = 0; u < E; ++u) { r[u].x *= p.scale; r[u].y *= p.scale; }
             }
         }
-        if (active) {
+        if constexpr (G == 1 && ((MODE == C_INV_PAIR && RMX_PAIR_BULK_STORE && (LOGE == 5 || RMX_PAIR_BULK_STORE > 1)) ||
+                                 (MODE == C_FWD && RMX_FWD_BULK_STORE && (LOGE == 5 || RMX_FWD_BULK_STORE > 1)))) {
+            // the row leaves through the exchange buffer and ONE bulk copy (TMA engine) instead of 32
+            // STG per thread: same shared-memory wavefronts as the stores' L1 wavefronts, but the warps
+            // do not sit in the LSU queue behind 64 KB of write-through traffic
+            __syncthreads();                                   // every thread is past its last exchange read
+#pragma unroll
+            for (int u = 0; u < E; ++u) smem[i0 + u * NT] = r[u];
+            fence_proxy_async();
+            __syncthreads();
+            if (threadIdx.x == 0 && active) {
+                bulk_store_1d(p.dst + item * p.src_item_stride + (row << LOGN), smem, (uint32_t)(GEO::N * sizeof(float2)));
+                bulk_store_wait_read();
+            }
+        } else if (active) {
             float2* __restrict__ out = p.dst + item * p.src_item_stride + (row << LOGN);
 #pragma unroll
             for (int u = 0; u < E; ++u) {
@@ -537,7 +570,10 @@ __global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run
         float2 r[E];
 #pragma unroll
         for (int u = 0; u < E; ++u) r[u] = cmul_conj(RMX_X_LOAD(xj + i0 + u * NT), a[u]);     // X_j * conj(X_i)
-        if (pidx != first) __syncthreads();                  // previous pair's last exchange read is done
+        if (pidx != first) {
+            if (RMX_PAIR_RUN_BULK_STORE && threadIdx.x == 0) bulk_store_wait_read();   // previous row has left the buffer
+            __syncthreads();
+        }
         fft_tile<GEO, true, (RMX_PAIR_TWTREE != 0)>(r, smem, g, i0, p.tabs);
         if (p.post_logm > 0) {
             float2 tw[E];
@@ -550,15 +586,25 @@ __global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run
             for (int u = 0; u < E; ++u) { r[u].x *= p.scale; r[u].y *= p.scale; }
         }
         float2* __restrict__ out = p.dst + (long long)pidx * p.src_item_stride + (row << LOGN);
+        if constexpr (RMX_PAIR_RUN_BULK_STORE) {
+            // row -> exchange buffer -> one bulk copy (TMA engine); it drains while the next pair loads
+            __syncthreads();                                 // every thread is past its last exchange read
 #pragma unroll
-        for (int u = 0; u < E; ++u) RMX_D_STORE(out + i0 + u * NT, r[u]);
+            for (int u = 0; u < E; ++u) smem[i0 + u * NT] = r[u];
+            fence_proxy_async();
+            __syncthreads();
+            if (threadIdx.x == 0) bulk_store_1d(out, smem, (uint32_t)(GEO::N * sizeof(float2)));
+        } else {
+#pragma unroll
+            for (int u = 0; u < E; ++u) RMX_D_STORE(out + i0 + u * NT, r[u]);
+        }
     }
+    if (RMX_PAIR_RUN_BULK_STORE && threadIdx.x == 0) bulk_store_wait_read();
 }
 
 // ---------------------------------------------------------------------------------------
 // TMA helpers (sm_100a): 2-D tiled bulk-tensor loads completing on an mbarrier
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -576,7 +622,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
             "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, unsigned long long* bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
