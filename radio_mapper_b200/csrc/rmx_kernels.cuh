@@ -351,8 +351,11 @@ k_contig(const PassParams p) {
                 for (int u = 0; u < E; ++u) { r[u].x *= p.scale; r[u].y *= p.scale; }
             }
         }
-        if constexpr (G == 1 && ((MODE == C_INV_PAIR && RMX_PAIR_BULK_STORE && (LOGE == 5 || RMX_PAIR_BULK_STORE > 1)) ||
-                                 (MODE == C_FWD && RMX_FWD_BULK_STORE && (LOGE == 5 || RMX_FWD_BULK_STORE > 1)))) {
+        constexpr bool BULK = G == 1 && ((MODE == C_INV_PAIR && RMX_PAIR_BULK_STORE && (LOGE == 5 || RMX_PAIR_BULK_STORE > 1)) ||
+                                         (MODE == C_FWD && RMX_FWD_BULK_STORE && (LOGE == 5 || RMX_FWD_BULK_STORE > 1)));
+        // cp.async.bulk needs a 16-byte aligned destination; rows are multiples of 32 KB apart, so only the
+        // base pointer matters (launch-uniform)
+        if (BULK && (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0) {
             // the row leaves through the exchange buffer and ONE bulk copy (TMA engine) instead of 32
             // STG per thread: same shared-memory wavefronts as the stores' L1 wavefronts, but the warps
             // do not sit in the LSU queue behind 64 KB of write-through traffic

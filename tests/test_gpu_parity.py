@@ -255,6 +255,23 @@ def test_xcorr_full_output_matches_scipy(rmx):
         assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 2e-6
 
 
+def test_xcorr_full_into_unaligned_output(rmx):
+    """The 8192-point row pass writes each row with one 16-byte-aligned bulk copy; an output tensor that is
+    only 8-byte aligned must take the per-thread store path and give the same bits."""
+    import torch
+    n = 1 << 22                                       # plan 1024 x 8192
+    iq, _, _ = synth.delayed_buoys(77, 2, n)
+    plan = rmx.Plan(2, n)
+    S = plan.forward(_cuda(iq))
+    pairs = _cuda(rmx.pair_table(2))
+    aligned = plan.xcorr_full(S, pairs)
+    backing = torch.empty(plan.fft_len + 1, dtype=torch.complex64, device="cuda")
+    view = backing[1:].view(1, plan.fft_len)
+    assert view.data_ptr() % 16 == 8
+    out = plan.xcorr_full(S, pairs, out=view)
+    assert torch.equal(out, aligned)
+
+
 def test_fractional_delay_accuracy(rmx):
     """Sub-sample delays: GPU frac == oracle frac within 1e-3, and both track the true delay."""
     fr = [0.0, 0.3, -0.2, 0.12]
