@@ -164,6 +164,17 @@ RMX_API int rmx_select_by_distance_host(const int32_t* positions, const float* h
  * replaces np.mean(...) signal_analyzer.py:75 and np.median(...) buoy_node.py:427 */
 RMX_API int rmx_mean_median(const float* db, int n, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Stage 5c/5d batched — block detection for many dB spectra at once (one CTA per row):
+ * scipy.signal.find_peaks(db_row, height=H, distance=D) with H = height (height_mode 0; buoy_node.py:411-415,
+ * iq_stream_client.py:197-201) or H = mean(db_row) + height (height_mode 1; signal_analyzer.py:75), plus the row's
+ * mean and median (buoy_node.py:427).  idx/heights: [n_rows][cap] kept peaks in ascending bin order and their
+ * dB values; count[row] = number of kept peaks (only the first cap are stored), or -(candidates) when a row has
+ * more than 16384 candidates before the distance rule (rows longer than 32768 bins can) (take that row through rmx_threshold_peaks instead);
+ * stats: [n_rows][2] = mean, median.  distance <= 1 disables the distance rule. */
+RMX_API int rmx_find_peaks_batch(const float* db, int n_rows, int n, size_t row_stride, float height, int height_mode,
+                         int distance, int32_t* idx, float* heights, int32_t* count, int cap, float* stats,
+                         void* stream);
+
 /* Per-launch timing with CUDA events on the launching stream (off by default).  enable != 0 clears
  * earlier records and starts recording; collect synchronises the recorded events and returns the
  * number of distinct kernel names written to out[0..cap). */

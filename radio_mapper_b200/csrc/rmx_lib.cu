@@ -1315,6 +1315,207 @@ extern "C" int rmx_mean_median(const float* db, int n, float* out, void* workspa
     return RMX_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// batched block detection: scipy.signal.find_peaks(height=, distance=) + mean/median per row
+// ---------------------------------------------------------------------------------------
+// One CTA (1024 threads) per dB spectrum.  (1) mean and median of the row (same arithmetic as
+// k_mean_median); (2) candidates = strict local maxima with plateau mid-points (_local_maxima_1d),
+// value >= threshold, compacted in ascending bin order; (3) the distance rule: candidates are ranked by
+// (height, position), visited from the highest priority down, and a kept candidate removes every
+// not-yet-visited neighbour closer than `distance` bins (_select_by_peak_distance; ties resolved like
+// rmx_select_by_distance_host); (4) the kept peaks, ascending, with their heights.
+constexpr int kPeakCap = 16384;         // candidates per row held in shared memory (a 32768-bin row has at most 16383)
+
+__device__ __forceinline__ int block_exclusive_scan_1024(int v, int* s_warp, int* total) {
+    // exclusive prefix sum of one int per thread over a 1024-thread block
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int x = s_warp[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += t;
+        }
+        s_warp[lane] = x;                 // inclusive over warps
+    }
+    __syncthreads();
+    const int base = w == 0 ? 0 : s_warp[w - 1];
+    *total = s_warp[31];
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(1024) k_find_peaks_batch(const float* __restrict__ db, int n, long long row_stride,
+                                                           float height, int height_mode, int distance,
+                                                           int32_t* __restrict__ idx_out, float* __restrict__ h_out,
+                                                           int32_t* __restrict__ count_out, int cap,
+                                                           float* __restrict__ stats_out, int smem_cap) {
+    extern __shared__ __align__(8) unsigned char s_dyn[];
+    // [smem_cap] each: (height key << 32 | candidate index) for the priority sort, candidate bin, keep flag
+    unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(s_dyn);
+    int32_t* s_pos = reinterpret_cast<int32_t*>(s_sort + smem_cap);
+    uint8_t* s_keep = reinterpret_cast<uint8_t*>(s_pos + smem_cap);
+    __shared__ unsigned hist[256];
+    __shared__ double s_sum[32];
+    __shared__ uint32_t s_prefix;
+    __shared__ unsigned s_rank;
+    __shared__ int s_warp[32];
+    __shared__ float s_stats[2];
+
+    const float* __restrict__ x = db + (long long)blockIdx.x * row_stride;
+    // ---- (1) mean, median -------------------------------------------------------------------
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)x[i];
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 32; ++w) t += s_sum[w];
+        s_stats[0] = (float)(t / (double)n);
+    }
+    float med[2];
+    for (int which = 0; which < 2; ++which) {
+        const unsigned rank0 = which == 0 ? (unsigned)((n - 1) / 2) : (unsigned)(n / 2);
+        if (threadIdx.x == 0) { s_prefix = 0; s_rank = rank0; }
+        __syncthreads();
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            const uint32_t mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint32_t k = float_order_key(x[i]);
+                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xffu], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned r = s_rank, b = 0;
+                while (b < 255 && r >= hist[b]) { r -= hist[b]; ++b; }
+                s_rank = r;
+                s_prefix = prefix | (b << shift);
+            }
+            __syncthreads();
+        }
+        med[which] = key_to_float(s_prefix);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        s_stats[1] = (n & 1) ? med[0] : 0.5f * (med[0] + med[1]);
+        stats_out[2 * blockIdx.x] = s_stats[0];
+        stats_out[2 * blockIdx.x + 1] = s_stats[1];
+    }
+    __syncthreads();
+    // threshold: absolute, or mean + height evaluated like the host does (double sum, rounded to float)
+    const float thr = height_mode ? (float)((double)s_stats[0] + (double)height) : height;
+
+    // ---- (2) candidates in ascending order: contiguous chunk of rising edges per thread -------
+    const int i_max = n - 1;
+    const int chunk = (max(i_max - 1, 0) + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int lo = 1 + (int)threadIdx.x * chunk, hi = min(lo + chunk, i_max);
+    int mine = 0;
+    for (int i = lo; i < hi; ++i) {
+        const float v = x[i];
+        if (!(x[i - 1] < v) || !(v >= thr)) continue;
+        int ahead = i + 1;
+        while (ahead < i_max && x[ahead] == v) ++ahead;
+        if (x[ahead] < v) ++mine;
+    }
+    int n_cand;
+    int at = block_exclusive_scan_1024(mine, s_warp, &n_cand);
+    if (n_cand > smem_cap) {                      // overflow: report the candidate count, no peaks
+        if (threadIdx.x == 0) count_out[blockIdx.x] = -n_cand;
+        return;
+    }
+    for (int i = lo; i < hi; ++i) {
+        const float v = x[i];
+        if (!(x[i - 1] < v) || !(v >= thr)) continue;
+        int ahead = i + 1;
+        while (ahead < i_max && x[ahead] == v) ++ahead;
+        if (x[ahead] < v) {
+            s_pos[at] = (i + ahead - 1) / 2;
+            s_sort[at] = ((unsigned long long)float_order_key(v) << 32) | (unsigned)at;
+            s_keep[at] = 1;
+            ++at;
+        }
+    }
+    __syncthreads();
+    // ---- (3) distance rule --------------------------------------------------------------------
+    if (distance > 1 && n_cand > 1) {
+        // priority order = ascending (height, position): bitonic sort of the 64-bit composites
+        int m = 1;
+        while (m < n_cand) m <<= 1;
+        for (int k = n_cand + (int)threadIdx.x; k < m; k += blockDim.x) s_sort[k] = ~0ULL;
+        __syncthreads();
+        for (int size = 2; size <= m; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+                    const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                    const int j = i | stride;
+                    const bool up = (i & size) == 0;
+                    const unsigned long long a = s_sort[i], b = s_sort[j];
+                    if ((a > b) == up) { s_sort[i] = b; s_sort[j] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        // visit from the highest priority down; a kept candidate removes its not-yet-visited neighbours
+        if (threadIdx.x == 0) {
+            for (int o = n_cand - 1; o >= 0; --o) {
+                const int j = (int)(unsigned)(s_sort[o] & 0xffffffffULL);
+                if (!s_keep[j]) continue;
+                const int pj = s_pos[j];
+                for (int k = j - 1; k >= 0 && pj - s_pos[k] < distance; --k) s_keep[k] = 0;
+                for (int k = j + 1; k < n_cand && s_pos[k] - pj < distance; ++k) s_keep[k] = 0;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- (4) kept peaks, ascending ---------------------------------------------------------------
+    const int per = (n_cand + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int k0 = (int)threadIdx.x * per, k1 = min(k0 + per, n_cand);
+    int kept = 0;
+    for (int k = k0; k < k1; ++k) kept += s_keep[k];
+    int total;
+    int w = block_exclusive_scan_1024(kept, s_warp, &total);
+    int32_t* __restrict__ io = idx_out + (long long)blockIdx.x * cap;
+    float* __restrict__ ho = h_out + (long long)blockIdx.x * cap;
+    for (int k = k0; k < k1; ++k)
+        if (s_keep[k]) {
+            if (w < cap) { io[w] = s_pos[k]; ho[w] = x[s_pos[k]]; }
+            ++w;
+        }
+    if (threadIdx.x == 0) count_out[blockIdx.x] = total;
+}
+
+extern "C" int rmx_find_peaks_batch(const float* db, int n_rows, int n, size_t row_stride, float height, int height_mode,
+                                    int distance, int32_t* idx, float* heights, int32_t* count, int cap, float* stats,
+                                    void* stream) {
+    if (!db || !idx || !heights || !count || !stats) return fail(RMX_ERR_ARG, "null argument to rmx_find_peaks_batch");
+    if (n_rows <= 0) return RMX_OK;
+    if (n < 1 || cap < 1) return fail(RMX_ERR_ARG, "rmx_find_peaks_batch needs n >= 1 and cap >= 1");
+    if (row_stride == 0) row_stride = (size_t)n;
+    if (row_stride < (size_t)n) return fail(RMX_ERR_ARG, "row_stride must be >= n");
+    // shared memory for as many candidates as a row can have (a strict local maximum every other bin), rounded
+    // up to a power of two for the bitonic sort and bounded by what one SM offers
+    int smem_cap = 1024;
+    while (smem_cap < n / 2 + 1 && smem_cap < kPeakCap) smem_cap <<= 1;
+    const size_t smem = (size_t)smem_cap * (sizeof(unsigned long long) + sizeof(int32_t) + 1);
+    CUDA_TRY(cudaFuncSetAttribute((const void*)k_find_peaks_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_find_peaks_batch<<<n_rows, 1024, smem, (cudaStream_t)stream>>>(db, n, (long long)row_stride, height, height_mode, distance,
+                                                                       idx, heights, count, cap, stats, smem_cap);
+    LAUNCH_CHECK("find_peaks_batch");
+    return RMX_OK;
+}
+
 // exact integer statistics: |x|^2 = ((2I-255)^2 + (2Q-255)^2) / 4
 __global__ void __launch_bounds__(256) k_signal_stats(const uint8_t* __restrict__ in, size_t n,
                                                       unsigned long long* __restrict__ acc) {

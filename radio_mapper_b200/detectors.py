@@ -132,6 +132,63 @@ class BuoySignalDetector:
         return bins, out
 
 
+    def detect_blocks_arrays(self, iq_u8, center_freq_mhz: float):
+        """Numeric half of `detect_blocks`: for uint8[n_blocks, 2N] (N a power of two >= 16; host or CUDA)
+        returns, per block, (bins int32[], frequency_hz float64[], power_db float32[], confidence float64[]) of
+        the detections that pass the reference's gates (|f - fc| >= 10 kHz, confidence >= 0.3;
+        buoy_node.py:423-433), in increasing bin order.  One batched forward FFT, one dB pass and one
+        find_peaks/median launch cover all blocks; only the peak lists come back to the host."""
+        import torch
+        eng = _engine()
+        t = torch.as_tensor(iq_u8)
+        if t.ndim != 2 or t.dtype != torch.uint8 or t.shape[1] % 2:
+            raise ValueError("iq_u8 must be uint8[n_blocks, 2N]")
+        nb, n = t.shape[0], t.shape[1] // 2
+        if not (eng.is_pow2(n) and n >= 16):
+            raise ValueError("detect_blocks_arrays needs a power-of-two block length >= 16 (use detect_block)")
+        key = (nb, n, n)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = eng.Plan(nb, n, n)
+        db = plan.spectrum_db(plan.forward(t.cuda(non_blocking=True)))         # [nb, n] dB, natural order
+        peaks, heights, _, medians = eng.find_peaks_batch(db, self.detection_threshold_dbm, 10,   # :411-415, :427
+                                                          cap=n // 10 + 2)
+        center_freq_hz = int(center_freq_mhz * 1e6)                            # :365
+        abs_freqs = np.fft.fftfreq(n, 1.0 / self.sample_rate) + center_freq_hz   # :402,408
+        out = []
+        for b in range(nb):
+            k = peaks[b]
+            f_hz = abs_freqs[k]
+            power = heights[b]
+            # same float32 arithmetic as the per-block loop: (power - median) / 20.0 promotes to float64
+            conf = np.minimum(np.maximum((power - medians[b]).astype(np.float32) / 20.0, 0.0), 1.0)
+            keep = (np.abs(f_hz - center_freq_hz) >= 10000) & (conf >= 0.3)
+            out.append((k[keep], f_hz[keep], power[keep], conf[keep]))
+        return out
+
+    def detect_blocks(self, iq_u8, center_freq_mhz: float, iso_timestamps: Optional[List[str]] = None,
+                      gps_ns: Optional[List[int]] = None) -> List[List[SignalDetection]]:
+        """`detect_block` for many raw cu8 blocks of one length at once (see `detect_blocks_arrays`)."""
+        import torch
+        eng = _engine()
+        t = torch.as_tensor(iq_u8)
+        nb = t.shape[0]
+        n = t.shape[1] // 2 if t.ndim == 2 else 0
+        if t.ndim != 2 or not (eng.is_pow2(n) and n >= 16):
+            return [self.detect_block(t[b], center_freq_mhz, iso_timestamps[b] if iso_timestamps else None,
+                                      gps_ns[b] if gps_ns else None) for b in range(nb)]
+        results: List[List[SignalDetection]] = []
+        for b, (bins, f_hz, power, conf) in enumerate(self.detect_blocks_arrays(t, center_freq_mhz)):
+            stamp = iso_timestamps[b] if iso_timestamps else datetime.now(timezone.utc).isoformat()
+            ns = gps_ns[b] if gps_ns else time.time_ns()
+            results.append([SignalDetection(buoy_id=self.buoy_id, frequency_mhz=round(f / 1e6, 3),
+                                            signal_strength_dbm=round(pw, 1), timestamp_utc=stamp,
+                                            gps_timestamp_ns=ns, lat=self.lat, lng=self.lng,
+                                            confidence=round(c, 2), signal_type=classify_buoy(f / 1e6))
+                            for f, pw, c in zip(f_hz, power, conf)])
+        return results
+
+
 @dataclass
 class StreamDetection:
     """Fields of iq_stream_client.SignalDetection (:46-60)."""

@@ -277,6 +277,47 @@ def threshold_peaks(db: torch.Tensor, height: float, cap: Optional[int] = None) 
     return np.sort(idx[:c].cpu().numpy())
 
 
+def find_peaks_batch(db: torch.Tensor, height: float, distance: int = 0, height_above_mean: bool = False, cap: int = 1024):
+    """scipy.signal.find_peaks(row, height=, distance=) for every row of db[n_rows, n] in one launch, plus each
+    row's mean and median.  height_above_mean=True uses mean(row) + height (signal_analyzer.py:75).
+    Returns (peaks: list of int32 arrays (ascending bins), heights: list of float32 arrays, mean[n_rows],
+    median[n_rows]) on the host; only the peak lists cross PCIe, not the spectra."""
+    _require_cuda(db, torch.float32, "db")
+    if db.ndim != 2:
+        raise ValueError("db must be [n_rows, n]")
+    n_rows, n = db.shape
+    if db.stride(1) != 1:
+        db = db.contiguous()
+    cap = max(1, int(cap))
+    dev = db.device
+    idx = torch.empty((n_rows, cap), dtype=torch.int32, device=dev)
+    hts = torch.empty((n_rows, cap), dtype=torch.float32, device=dev)
+    count = torch.empty(n_rows, dtype=torch.int32, device=dev)
+    stats = torch.empty((n_rows, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _native.check(_lib.rmx_find_peaks_batch(_ptr(db), n_rows, n, db.stride(0), float(height), int(bool(height_above_mean)),
+                                                int(np.ceil(distance)) if distance else 0, _ptr(idx), _ptr(hts), _ptr(count),
+                                                cap, _ptr(stats), _stream_ptr()), "rmx_find_peaks_batch")
+    c = count.cpu().numpy()
+    st = stats.cpu().numpy()
+    most = int(min(cap, max(0, c.max(initial=0))))
+    idx_h = idx[:, :most].cpu().numpy() if most else np.empty((n_rows, 0), np.int32)
+    hts_h = hts[:, :most].cpu().numpy() if most else np.empty((n_rows, 0), np.float32)
+    peaks, heights = [], []
+    for r in range(n_rows):
+        if c[r] < 0 or c[r] > cap:
+            # more candidates than the kernel keeps on chip (or more peaks than `cap`): this row alone goes
+            # through the single-row entry points
+            thr = float(st[r, 0]) + float(height) if height_above_mean else float(height)
+            cand = threshold_peaks(db[r], thr)
+            row = db[r].cpu().numpy()
+            kept = select_by_distance(cand, row[cand], distance) if distance else cand
+            peaks.append(kept.astype(np.int32)); heights.append(row[kept])
+        else:
+            peaks.append(idx_h[r, :c[r]].copy()); heights.append(hts_h[r, :c[r]].copy())
+    return peaks, heights, st[:, 0].copy(), st[:, 1].copy()
+
+
 def select_by_distance(positions: np.ndarray, heights: np.ndarray, distance: int) -> np.ndarray:
     """find_peaks(distance=) greedy rule on host arrays; returns the kept positions."""
     positions = np.ascontiguousarray(positions, dtype=np.int32)

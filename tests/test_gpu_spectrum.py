@@ -293,3 +293,72 @@ def test_correlate_iq_end_to_end():
     assert np.array_equal(a["lag"], b["lag"]) and a.shape == (2, 6)
     with pytest.raises(ValueError):
         proc.correlate_iq(block, ids[:3], fs, 121.5)
+
+
+# ---- batched block detection ----------------------------------------------
+@pytest.mark.parametrize("distance", [0, 1, 3, 10, 57])
+def test_find_peaks_batch_matches_scipy(rmx, distance):
+    """Every row of a batch against scipy.signal.find_peaks itself: noise rows, rows quantised to few
+    levels (plateaus and exact ties in height), a constant row, a monotone row, and both height modes."""
+    rng = np.random.default_rng(40 + distance)
+    n = 4096
+    rows = [rng.standard_normal(n).astype(np.float32) for _ in range(5)]
+    rows += [np.round(rng.standard_normal(n) * 2).astype(np.float32) for _ in range(4)]      # plateaus, ties
+    rows += [np.zeros(n, np.float32), np.arange(n, dtype=np.float32), -np.arange(n, dtype=np.float32)]
+    rows.append(np.repeat(rng.standard_normal(n // 8), 8).astype(np.float32))                # wide plateaus
+    db = np.stack(rows)
+    for above_mean, height in ((False, 0.25), (True, 0.5)):
+        peaks, heights, mean, median = rmx.find_peaks_batch(_cuda(db), height, distance, height_above_mean=above_mean,
+                                                            cap=n // 2 + 1)
+        for r, row in enumerate(db):
+            h = np.float32(np.float32(row.mean(dtype=np.float64)) + height) if above_mean else height
+            kw = {"distance": distance} if distance >= 1 else {}
+            want, _ = scipy.signal.find_peaks(row, height=h, **kw)
+            ties = len(np.unique(row[want])) != len(want) if distance > 1 else False
+            if not ties:
+                assert np.array_equal(peaks[r], want), (r, distance, above_mean)
+                assert np.array_equal(heights[r], row[want])
+            else:
+                # equal heights: scipy's argsort order is unspecified; both answers obey the distance rule
+                assert len(peaks[r]) == 0 or np.all(np.diff(peaks[r]) >= distance)
+            assert abs(mean[r] - row.mean(dtype=np.float64)) <= 1e-6 * max(1.0, abs(row.mean()))
+            assert median[r] == np.median(row)
+
+
+def test_find_peaks_batch_overflow_row_falls_back(rmx):
+    """A row with more candidates than fit in shared memory (> 16384: only rows longer than 32768 bins can)
+    is reported by the kernel and finished by the single-row path."""
+    rng = np.random.default_rng(3)
+    n = 65536
+    saw = np.tile(np.array([0.0, 1.0], np.float32), n // 2) + rng.random(n).astype(np.float32) * 0.01   # ~16k maxima
+    quiet = rng.standard_normal(n).astype(np.float32) - 10.0
+    db = np.stack([saw, quiet])
+    peaks, heights, _, _ = rmx.find_peaks_batch(_cuda(db), 0.5, 10, cap=8192)
+    assert len(peaks[0]) > 3000 and len(peaks[1]) == 0
+    for r in range(2):
+        want, _ = scipy.signal.find_peaks(db[r], height=0.5, distance=10)
+        assert np.array_equal(peaks[r], want)
+        assert np.array_equal(heights[r], db[r][want])
+
+
+def test_buoy_detect_blocks_equals_per_block(golden_dir):
+    """detect_blocks (one batched launch chain) == detect_block on each block, including the reference's
+    golden block; mixed content so blocks differ in peak count."""
+    from radio_mapper_b200.detectors import BuoySignalDetector
+    g = np.load(os.path.join(golden_dir, "buoy_detect.npz"))
+    n2 = g["iq"].size
+    rng = np.random.default_rng(8)
+    blocks = [g["iq"]]
+    for k in range(6):
+        u, _ = synth.welch_stream(100 + k, 1, n2 // 2)
+        blocks.append(u[:n2])
+    blocks.append(rng.integers(0, 256, n2, dtype=np.uint8))
+    iq = np.stack(blocks)
+    det = BuoySignalDetector("BUOY_T", 35.4676, -97.5164)
+    stamps = ["2026-01-01T00:00:%02dZ" % b for b in range(len(blocks))]
+    ns = list(range(1000, 1000 + len(blocks)))
+    batched = det.detect_blocks(iq, float(g["center_mhz"]), stamps, ns)
+    for b in range(len(blocks)):
+        single = det.detect_block(iq[b], float(g["center_mhz"]), stamps[b], ns[b])
+        assert batched[b] == single, b
+    assert sum(len(x) for x in batched) > 0
