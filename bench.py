@@ -312,6 +312,41 @@ def run_b200(args, wl):
     assert len(meas) == W * P
     e2e_value = P * N * W * world * args.steps / e2e_s
 
+    # ---- the same windows through the streaming API (ingest.ArraySource -> pinned ring -> copy stream ->
+    #      correlator): the copy of window w+1 overlaps the kernels of window w across step boundaries too ----
+    stream_value = None
+    if rank == 0 and world == 1:
+        from radio_mapper_b200 import ingest
+        src_np = iq_host.view(B, -1)                                    # pinned uint8[B, W*2N]: windows are consecutive
+        n_meas = sum(len(m) for m in proc.correlate_stream(ingest.ArraySource(src_np, N), buoy_ids, fs, 121.5, depth=3))
+        torch.cuda.synchronize()
+
+        class _Repeat:                                                  # args.steps passes over the same bytes
+            def __init__(self, a, n, reps):
+                self.inner = ingest.ArraySource(a, n)
+                self.n_buoys, self.samples_per_window = self.inner.n_buoys, n
+                self.n_windows = self.inner.n_windows * reps
+
+            def read_window(self, w, out):
+                return w < self.n_windows and self.inner.read_window(w % self.inner.n_windows, out)
+
+            def pinned_window(self, w):
+                return self.inner.pinned_window(w % self.inner.n_windows) if w < self.n_windows else None
+
+            def close(self):
+                pass
+
+        t0 = time.perf_counter()
+        n_meas = 0
+        for m in proc.correlate_stream(_Repeat(src_np, N, args.steps), buoy_ids, fs, 121.5, depth=3):
+            n_meas += len(m)
+        torch.cuda.synchronize()
+        stream_s = time.perf_counter() - t0
+        assert n_meas == W * P * args.steps
+        stream_value = {"value": P * N * W * args.steps / stream_s, "unit": UNIT, "ms_per_step": 1e3 * stream_s / args.steps,
+                        "api": "TDoAProcessor.correlate_stream(ingest source, ...) -> TDoAMeasurements per window",
+                        "note": "pinned source: windows are DMA'd in place; file / pipe sources add one host copy into the pinned ring"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -398,6 +433,7 @@ def run_b200(args, wl):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(iq_host.numel()),
                 "d2h_bytes_per_step": int(W * P * 16 + W * B * 8), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "streaming": stream_value,
                 "api": "TDoAProcessor.correlate_iq(pinned host uint8[B,W,2N]) -> List[TDoAMeasurement]"},
         "gpu_launches": launches,
         "roofline": roofline,
