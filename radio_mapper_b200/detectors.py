@@ -151,20 +151,26 @@ class BuoySignalDetector:
         if plan is None:
             plan = self._plans[key] = eng.Plan(nb, n, n)
         db = plan.spectrum_db(plan.forward(t.cuda(non_blocking=True)))         # [nb, n] dB, natural order
-        peaks, heights, _, medians = eng.find_peaks_batch(db, self.detection_threshold_dbm, 10,   # :411-415, :427
-                                                          cap=n // 10 + 2)
+        try:
+            bins, power, off, _, medians = eng.find_peaks_batch(db, self.detection_threshold_dbm, 10,   # :411-415, :427
+                                                                cap=n // 10 + 2, flat=True)
+        except eng._native.RmxError:
+            peaks, heights, _, medians = eng.find_peaks_batch(db, self.detection_threshold_dbm, 10, cap=n // 10 + 2)
+            bins, power = np.concatenate(peaks), np.concatenate(heights)
+            off = np.concatenate([[0], np.cumsum([len(p) for p in peaks])])
         center_freq_hz = int(center_freq_mhz * 1e6)                            # :365
         abs_freqs = np.fft.fftfreq(n, 1.0 / self.sample_rate) + center_freq_hz   # :402,408
-        out = []
-        for b in range(nb):
-            k = peaks[b]
-            f_hz = abs_freqs[k]
-            power = heights[b]
-            # same float32 arithmetic as the per-block loop: (power - median) / 20.0 promotes to float64
-            conf = np.minimum(np.maximum((power - medians[b]).astype(np.float32) / 20.0, 0.0), 1.0)
-            keep = (np.abs(f_hz - center_freq_hz) >= 10000) & (conf >= 0.3)
-            out.append((k[keep], f_hz[keep], power[keep], conf[keep]))
-        return out
+        # gates of buoy_node.py:423-433 on all blocks at once (same float32 arithmetic as the per-block loop:
+        # power - median in float32, / 20.0 in float64)
+        f_hz = abs_freqs[bins]
+        med = np.repeat(medians, np.diff(off))
+        conf = np.minimum(np.maximum((power - med).astype(np.float32) / 20.0, 0.0), 1.0)
+        keep = (np.abs(f_hz - center_freq_hz) >= 10000) & (conf >= 0.3)
+        kept_per_block = np.add.reduceat(np.concatenate([keep, [False]]).astype(np.int64), off[:-1]) if len(keep) else np.zeros(nb, np.int64)
+        kept_per_block = np.where(np.diff(off) > 0, kept_per_block, 0)
+        cuts = np.cumsum(kept_per_block)[:-1]
+        return list(zip(np.split(bins[keep], cuts), np.split(f_hz[keep], cuts), np.split(power[keep], cuts),
+                        np.split(conf[keep], cuts)))
 
     def detect_blocks(self, iq_u8, center_freq_mhz: float, iso_timestamps: Optional[List[str]] = None,
                       gps_ns: Optional[List[int]] = None) -> List[List[SignalDetection]]:

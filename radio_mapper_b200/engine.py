@@ -277,11 +277,16 @@ def threshold_peaks(db: torch.Tensor, height: float, cap: Optional[int] = None) 
     return np.sort(idx[:c].cpu().numpy())
 
 
-def find_peaks_batch(db: torch.Tensor, height: float, distance: int = 0, height_above_mean: bool = False, cap: int = 1024):
+_pinned_peaks: dict = {}
+
+
+def find_peaks_batch(db: torch.Tensor, height: float, distance: int = 0, height_above_mean: bool = False, cap: int = 1024,
+                     flat: bool = False):
     """scipy.signal.find_peaks(row, height=, distance=) for every row of db[n_rows, n] in one launch, plus each
     row's mean and median.  height_above_mean=True uses mean(row) + height (signal_analyzer.py:75).
     Returns (peaks: list of int32 arrays (ascending bins), heights: list of float32 arrays, mean[n_rows],
-    median[n_rows]) on the host; only the peak lists cross PCIe, not the spectra."""
+    median[n_rows]) on the host; only the peak lists cross PCIe, not the spectra.  flat=True returns
+    (bins, heights, offsets[n_rows + 1], mean, median) with row r in [offsets[r], offsets[r+1])."""
     _require_cuda(db, torch.float32, "db")
     if db.ndim != 2:
         raise ValueError("db must be [n_rows, n]")
@@ -301,11 +306,36 @@ def find_peaks_batch(db: torch.Tensor, height: float, distance: int = 0, height_
     c = count.cpu().numpy()
     st = stats.cpu().numpy()
     most = int(min(cap, max(0, c.max(initial=0))))
-    idx_h = idx[:, :most].cpu().numpy() if most else np.empty((n_rows, 0), np.int32)
-    hts_h = hts[:, :most].cpu().numpy() if most else np.empty((n_rows, 0), np.float32)
+    if most:
+        # page-locked staging (cached per shape): the peak lists are tens of MB for a large batch
+        key = (n_rows, cap)
+        stage = _pinned_peaks.get(key)
+        if stage is None:
+            if len(_pinned_peaks) > 4:
+                _pinned_peaks.clear()
+            stage = _pinned_peaks[key] = (torch.empty((n_rows, cap), dtype=torch.int32).pin_memory(),
+                                          torch.empty((n_rows, cap), dtype=torch.float32).pin_memory())
+        with torch.cuda.device(dev):
+            stage[0][:, :most].copy_(idx[:, :most], non_blocking=True)
+            stage[1][:, :most].copy_(hts[:, :most], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        idx_h, hts_h = stage[0][:, :most].numpy(), stage[1][:, :most].numpy()
+    else:
+        idx_h, hts_h = np.empty((n_rows, 0), np.int32), np.empty((n_rows, 0), np.float32)
+    ok = (c >= 0) & (c <= cap)
+    if flat:
+        # one boolean mask over the [n_rows, most] block instead of a Python loop over rows
+        cc = np.where(ok, c, 0)
+        mask = np.arange(most)[None, :] < cc[:, None]
+        flat_bins, flat_h = idx_h[mask], hts_h[mask]
+        offsets = np.concatenate([[0], np.cumsum(cc)])
+        if not ok.all():
+            raise _native.RmxError("find_peaks_batch(flat=True): %d rows exceed the on-chip candidate limit or cap"
+                                   % int((~ok).sum()))
+        return flat_bins, flat_h, offsets, st[:, 0].copy(), st[:, 1].copy()
     peaks, heights = [], []
     for r in range(n_rows):
-        if c[r] < 0 or c[r] > cap:
+        if not ok[r]:
             # more candidates than the kernel keeps on chip (or more peaks than `cap`): this row alone goes
             # through the single-row entry points
             thr = float(st[r, 0]) + float(height) if height_above_mean else float(height)
