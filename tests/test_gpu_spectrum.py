@@ -362,3 +362,21 @@ def test_buoy_detect_blocks_equals_per_block(golden_dir):
         single = det.detect_block(iq[b], float(g["center_mhz"]), stamps[b], ns[b])
         assert batched[b] == single, b
     assert sum(len(x) for x in batched) > 0
+
+
+@pytest.mark.parametrize("n_buoys", [8, 9, 12])
+def test_correlate_iq_split_first_window_matches_device_path(n_buoys):
+    """From pinned host memory the first window is processed in two halves while its second half is still
+    being copied; the records must be bit-identical to the all-at-once device path, for every window."""
+    import torch
+    from radio_mapper_b200.tdoa_processor import TDoAProcessor
+    n, W = 1 << 14, 3
+    iq, delays = synth.delayed_buoys_torch(50 + n_buoys, n_buoys, W, n, torch.device("cpu"))
+    proc = TDoAProcessor()
+    pinned = proc.correlate_iq_records(iq.pin_memory())
+    device = proc.correlate_iq_records(iq.cuda())
+    pageable = proc.correlate_iq_records(iq.numpy())
+    assert pinned.tobytes() == device.tobytes() == pageable.tobytes()
+    pairs = [(i, j) for i in range(n_buoys) for j in range(i + 1, n_buoys)]
+    for w in range(W):
+        assert list(pinned["lag"][w]) == [int(delays[w, j] - delays[w, i]) for i, j in pairs]
