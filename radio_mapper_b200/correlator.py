@@ -110,46 +110,62 @@ class Correlator:
         records = torch.empty((len(windows), pairs.shape[0], 4), dtype=torch.int32, device=self.device)
         energy = torch.empty((len(windows), self.n_buoys), dtype=torch.int64, device=self.device)
         self._copy_stream.wait_stream(compute)              # staging may still be read by earlier kernels
-        # The first window has nothing to hide its copy behind, so it is cut in two: the buoys of the first half
-        # are transformed and correlated among themselves while the second half is still on the bus.
-        split = pair_slice is None and self.n_buoys >= 8 and len(windows) > 0 and iq_u8.is_pinned()
-        half = self.n_buoys // 2
-        events, ev_half = [], None
+        # The first window has nothing to hide its copy behind, so it is cut into growing groups of buoys
+        # (2, 2, 4, 8, ...): each group is transformed, and correlated with everything already on the device,
+        # while the next group is still on the bus.
+        split = pair_slice is None and self.n_buoys >= 4 and len(windows) > 0 and iq_u8.is_pinned()
+        cuts = self._split_cuts() if split else []
+        events, cut_events = [], []
         with torch.cuda.stream(self._copy_stream):
             for k, w in enumerate(windows):
                 for b in range(self.n_buoys):               # contiguous rows: plain async memcpys
                     self._staging[b, w].copy_(iq_u8[b, w], non_blocking=True)
-                    if split and k == 0 and b == half - 1:
-                        ev_half = torch.cuda.Event()
-                        ev_half.record(self._copy_stream)
+                    if split and k == 0 and (b + 1) in cuts:
+                        ev = torch.cuda.Event()
+                        ev.record(self._copy_stream)
+                        cut_events.append(ev)
                 ev = torch.cuda.Event()
                 ev.record(self._copy_stream)
                 events.append(ev)
         for k, w in enumerate(windows):
             if split and k == 0:
-                self._run_split_window(w, half, ev_half, events[0], records[0], energy[0])
+                self._run_split_window(w, cuts, cut_events, records[0], energy[0])
                 continue
             compute.wait_event(events[k])
             self.run_device(self._staging, [w], pair_slice, records=records[k:k + 1], energy=energy[k:k + 1], pairs=pairs)
         return records, energy
 
-    def _run_split_window(self, w: int, half: int, ev_half, ev_full, records_w: torch.Tensor, energy_w: torch.Tensor):
-        """One window in two steps: buoys [0, half) as soon as their bytes are on the device (forward FFT,
-        energy, the pairs among them), then the rest and every remaining pair.  Same kernels on the same
-        spectra as run_device, so the records are identical."""
+    def _split_cuts(self):
+        """Group boundaries 2, 4, 8, ... , n_buoys (the last group takes the remainder)."""
+        cuts, c = [], 2
+        while c < self.n_buoys:
+            cuts.append(c)
+            c *= 2
+        cuts.append(self.n_buoys)
+        return cuts
+
+    def _run_split_window(self, w: int, cuts, cut_events, records_w: torch.Tensor, energy_w: torch.Tensor):
+        """One window group by group: buoys [first, cut) as soon as their bytes are on the device (forward FFT,
+        energy), then every pair (i < j) with first <= j < cut.  Same kernels on the same spectra as
+        run_device, so the records are identical."""
         compute = torch.cuda.current_stream()
         stream = ctypes.c_void_p(compute.cuda_stream)
-        if self._split is None or self._split[0] != half:
-            lo = np.nonzero(self.pairs_host[:, 1] < half)[0]                 # i < j < half
-            hi = np.nonzero(self.pairs_host[:, 1] >= half)[0]
+        if self._split is None:
             dev = self.device
-            self._split = (half, engine.Plan(half, self.n_samples, device=dev), engine.Plan(self.n_buoys - half, self.n_samples, device=dev),
-                           torch.from_numpy(lo).to(dev), torch.from_numpy(hi).to(dev),
-                           self.pairs[torch.from_numpy(lo).to(dev)].contiguous(), self.pairs[torch.from_numpy(hi).to(dev)].contiguous())
-        _, plan_lo, plan_hi, idx_lo, idx_hi, pairs_lo, pairs_hi = self._split
+            groups, first = [], 0
+            plans = {}
+            for cut in cuts:
+                count = cut - first
+                if count not in plans:
+                    plans[count] = engine.Plan(count, self.n_samples, device=dev)
+                sel = np.nonzero((self.pairs_host[:, 1] >= first) & (self.pairs_host[:, 1] < cut))[0]
+                idx = torch.from_numpy(sel).to(dev)
+                groups.append((first, count, plans[count], idx, self.pairs[idx].contiguous()))
+                first = cut
+            self._split = groups
         view = self._staging[:, w, :]
-        for first, count, plan, ev, idx, prs in ((0, half, plan_lo, ev_half, idx_lo, pairs_lo),
-                                                 (half, self.n_buoys - half, plan_hi, ev_full, idx_hi, pairs_hi)):
+        n_passes = len(self.plan.pass_lengths)
+        for (first, count, plan, idx, prs), ev in zip(self._split, cut_events):
             compute.wait_event(ev)
             part = view[first:first + count]
             plan.forward(part, out=self.spectra[first:first + count])
@@ -158,8 +174,7 @@ class Correlator:
                           "rmx_signal_energy")
             rec = self.plan.xcorr_pairs_peak(self.spectra, prs, max_pairs_in_flight=self.workspace_pairs)
             records_w.index_copy_(0, idx, rec)
-        n_passes = len(self.plan.pass_lengths)
-        self.launches += 2 * (n_passes + 1 + n_passes + 1 + 1)
+            self.launches += n_passes + 1 + n_passes + 1 + 1
 
     def _finish(self, rec: np.ndarray, energy_x4: np.ndarray) -> np.ndarray:
         out = np.empty(rec.shape[:2], dtype=RECORD_DTYPE)
