@@ -363,10 +363,25 @@ def run_b200(args, wl):
     pair_gbs = pair_b * n_calls / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else 0.0
     whole_gbs = total_b * W * args.steps / (elapsed_ms * 1e-3) / 1e9
     traffic, traffic_src = measured_traffic(args.workload, B, P, L)
+    per_kernel = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f)[args.workload]
+        unit = 8 * L
+        kb = {"contig_inv_pair": unit * (B * tr["pair_pass_read_per_buoy_unit8L"] + P * tr["pair_pass_write_per_pair_unit8L"]),
+              "col_inv_argmax": unit * P * tr["argmax_pass_read_per_pair_unit8L"]}
+        per_kernel = {}
+        for name, nbytes in kb.items():
+            if name in prof and prof[name][1] > 0:
+                ms = prof[name][1] / n_calls
+                per_kernel[name] = {"ms_per_launch": ms, "dram_bytes_per_launch": int(nbytes),
+                                    "dram_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_of_peak": nbytes / (ms * 1e-3) / 1e9 / peak}
+    except Exception:
+        per_kernel = None
     roofline = {
         "bound": "hbm", "kernel": "correlate+peak stage (" + " + ".join(sorted(pair_names)) + ")",
         "achieved": pair_gbs, "peak": peak, "unit": "GB/s", "frac": pair_gbs / peak, "traffic": traffic,
-        "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": pair_b,
+        "traffic_source": traffic_src, "per_kernel_dram": per_kernel, "peak_source": peak_src, "algorithmic_bytes_per_launch": pair_b,
         "avg_launch_ms": pair_ms / max(1, n_calls), "share_of_step": pair_ms / max(1e-9, pair_ms + fwd_ms),
         "whole_step": {"achieved": whole_gbs, "frac": whole_gbs / peak, "algorithmic_bytes_per_window": total_b},
         "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items())},
