@@ -170,10 +170,13 @@ RMX_API int rmx_mean_median(const float* db, int n, float* out, void* workspace,
  * mean and median (buoy_node.py:427).  idx/heights: [n_rows][cap] kept peaks in ascending bin order and their
  * dB values; count[row] = number of kept peaks (only the first cap are stored), or -(candidates) when a row has
  * more than 16384 candidates before the distance rule (rows longer than 32768 bins can) (take that row through rmx_threshold_peaks instead);
- * stats: [n_rows][2] = mean, median.  distance <= 1 disables the distance rule. */
+ * stats: [n_rows][2] = mean, median.  distance <= 1 disables the distance rule.
+ * Optional gates applied after the distance rule (buoy_node.py:423-433): gate_dc_bins > 0 drops peaks whose bin is
+ * closer than that to DC (bins k and n-k; the reference's |f - fc| < 10 kHz), gate_conf_min > 0 drops peaks with
+ * clip((p - median)/20, 0, 1) < gate_conf_min (float32 arithmetic). */
 RMX_API int rmx_find_peaks_batch(const float* db, int n_rows, int n, size_t row_stride, float height, int height_mode,
-                         int distance, int32_t* idx, float* heights, int32_t* count, int cap, float* stats,
-                         void* stream);
+                         int distance, int gate_dc_bins, float gate_conf_min, int32_t* idx, float* heights,
+                         int32_t* count, int cap, float* stats, void* stream);
 
 /* Per-launch timing with CUDA events on the launching stream (off by default).  enable != 0 clears
  * earlier records and starts recording; collect synchronises the recorded events and returns the

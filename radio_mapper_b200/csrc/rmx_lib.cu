@@ -1357,7 +1357,8 @@ __global__ void __launch_bounds__(1024) k_find_peaks_batch(const float* __restri
                                                            float height, int height_mode, int distance,
                                                            int32_t* __restrict__ idx_out, float* __restrict__ h_out,
                                                            int32_t* __restrict__ count_out, int cap,
-                                                           float* __restrict__ stats_out, int smem_cap) {
+                                                           float* __restrict__ stats_out, int smem_cap,
+                                                           int gate_dc_bins, float gate_conf_min) {
     extern __shared__ __align__(8) unsigned char s_dyn[];
     // [smem_cap] each: (height key << 32 | candidate index) for the priority sort, candidate bin, keep flag
     unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(s_dyn);
@@ -1479,6 +1480,19 @@ __global__ void __launch_bounds__(1024) k_find_peaks_batch(const float* __restri
         }
         __syncthreads();
     }
+    // optional gates of the buoy detector (buoy_node.py:423-433), applied AFTER the distance rule like the
+    // reference's loop over find_peaks' output: drop bins closer than gate_dc_bins to DC (|f - fc| < 10 kHz) and
+    // peaks whose confidence clip((p - median) / 20, 0, 1) is below gate_conf_min (float32 arithmetic, as numpy)
+    if (gate_dc_bins > 0 || gate_conf_min > 0.f) {
+        const float median = s_stats[1];
+        for (int k = threadIdx.x; k < n_cand; k += blockDim.x) {
+            if (!s_keep[k]) continue;
+            const int pos = s_pos[k];
+            const float conf = fminf(fmaxf((x[pos] - median) / 20.0f, 0.0f), 1.0f);
+            if (min(pos, n - pos) < gate_dc_bins || conf < gate_conf_min) s_keep[k] = 0;
+        }
+        __syncthreads();
+    }
     // ---- (4) kept peaks, ascending ---------------------------------------------------------------
     const int per = (n_cand + (int)blockDim.x - 1) / (int)blockDim.x;
     const int k0 = (int)threadIdx.x * per, k1 = min(k0 + per, n_cand);
@@ -1497,8 +1511,8 @@ __global__ void __launch_bounds__(1024) k_find_peaks_batch(const float* __restri
 }
 
 extern "C" int rmx_find_peaks_batch(const float* db, int n_rows, int n, size_t row_stride, float height, int height_mode,
-                                    int distance, int32_t* idx, float* heights, int32_t* count, int cap, float* stats,
-                                    void* stream) {
+                                    int distance, int gate_dc_bins, float gate_conf_min, int32_t* idx, float* heights,
+                                    int32_t* count, int cap, float* stats, void* stream) {
     if (!db || !idx || !heights || !count || !stats) return fail(RMX_ERR_ARG, "null argument to rmx_find_peaks_batch");
     if (n_rows <= 0) return RMX_OK;
     if (n < 1 || cap < 1) return fail(RMX_ERR_ARG, "rmx_find_peaks_batch needs n >= 1 and cap >= 1");
@@ -1511,7 +1525,7 @@ extern "C" int rmx_find_peaks_batch(const float* db, int n_rows, int n, size_t r
     const size_t smem = (size_t)smem_cap * (sizeof(unsigned long long) + sizeof(int32_t) + 1);
     CUDA_TRY(cudaFuncSetAttribute((const void*)k_find_peaks_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_find_peaks_batch<<<n_rows, 1024, smem, (cudaStream_t)stream>>>(db, n, (long long)row_stride, height, height_mode, distance,
-                                                                       idx, heights, count, cap, stats, smem_cap);
+                                                                       idx, heights, count, cap, stats, smem_cap, gate_dc_bins, gate_conf_min);
     LAUNCH_CHECK("find_peaks_batch");
     return RMX_OK;
 }

@@ -131,10 +131,9 @@ class BuoySignalDetector:
                                        confidence=round(confidence, 2), signal_type=classify_buoy(f_mhz)))
         return bins, out
 
-
     def detect_blocks_arrays(self, iq_u8, center_freq_mhz: float):
         """Numeric half of `detect_blocks`: for uint8[n_blocks, 2N] (N a power of two >= 16; host or CUDA)
-        returns, per block, (bins int32[], frequency_hz float64[], power_db float32[], confidence float64[]) of
+        returns, per block, (bins int32[], frequency_hz float64[], power_db float32[], confidence float32[]) of
         the detections that pass the reference's gates (|f - fc| >= 10 kHz, confidence >= 0.3;
         buoy_node.py:423-433), in increasing bin order.  One batched forward FFT, one dB pass and one
         find_peaks/median launch cover all blocks; only the peak lists come back to the host."""
@@ -151,24 +150,33 @@ class BuoySignalDetector:
         if plan is None:
             plan = self._plans[key] = eng.Plan(nb, n, n)
         db = plan.spectrum_db(plan.forward(t.cuda(non_blocking=True)))         # [nb, n] dB, natural order
-        try:
-            bins, power, off, _, medians = eng.find_peaks_batch(db, self.detection_threshold_dbm, 10,   # :411-415, :427
-                                                                cap=n // 10 + 2, flat=True)
-        except eng._native.RmxError:
-            peaks, heights, _, medians = eng.find_peaks_batch(db, self.detection_threshold_dbm, 10, cap=n // 10 + 2)
-            bins, power = np.concatenate(peaks), np.concatenate(heights)
-            off = np.concatenate([[0], np.cumsum([len(p) for p in peaks])])
         center_freq_hz = int(center_freq_mhz * 1e6)                            # :365
         abs_freqs = np.fft.fftfreq(n, 1.0 / self.sample_rate) + center_freq_hz   # :402,408
-        # gates of buoy_node.py:423-433 on all blocks at once (same float32 arithmetic as the per-block loop:
-        # power - median in float32, / 20.0 in float64)
+        # The |f - fc| < 10 kHz gate (:423) is a symmetric band of bins around DC; when the float64 mask really has
+        # that shape both gates run on the device and only the detections come back.
+        dc_mask = np.abs(abs_freqs - center_freq_hz) < 10000
+        ar = np.arange(n)
+        dc_bins = int(dc_mask[:n // 2].sum())
+        on_device = bool(np.array_equal(dc_mask, np.minimum(ar, n - ar) < dc_bins))
+        kw = dict(gate_dc_bins=dc_bins, gate_conf_min=0.3) if on_device else {}
+        try:
+            bins, power, off, _, medians = eng.find_peaks_batch(db, self.detection_threshold_dbm, 10,   # :411-415, :427
+                                                                cap=n // 10 + 2, flat=True, **kw)
+        except eng._native.RmxError:
+            peaks, heights, _, medians = eng.find_peaks_batch(db, self.detection_threshold_dbm, 10, cap=n // 10 + 2, **kw)
+            bins = np.concatenate(peaks) if peaks else np.empty(0, np.int32)
+            power = np.concatenate(heights) if heights else np.empty(0, np.float32)
+            off = np.concatenate([[0], np.cumsum([len(p) for p in peaks])])
+        # same float32 arithmetic as the per-block loop (:427-429)
         f_hz = abs_freqs[bins]
         med = np.repeat(medians, np.diff(off))
-        conf = np.minimum(np.maximum((power - med).astype(np.float32) / 20.0, 0.0), 1.0)
-        keep = (np.abs(f_hz - center_freq_hz) >= 10000) & (conf >= 0.3)
-        kept_per_block = np.add.reduceat(np.concatenate([keep, [False]]).astype(np.int64), off[:-1]) if len(keep) else np.zeros(nb, np.int64)
-        kept_per_block = np.where(np.diff(off) > 0, kept_per_block, 0)
-        cuts = np.cumsum(kept_per_block)[:-1]
+        conf = np.minimum(np.maximum((power - med) / np.float32(20.0), np.float32(0.0)), np.float32(1.0))
+        if on_device:
+            cuts = off[1:-1]
+            return list(zip(np.split(bins, cuts), np.split(f_hz, cuts), np.split(power, cuts), np.split(conf, cuts)))
+        keep = (~dc_mask[bins]) & (conf >= np.float32(0.3))
+        block_of = np.repeat(np.arange(nb), np.diff(off))
+        cuts = np.cumsum(np.bincount(block_of[keep], minlength=nb))[:-1]
         return list(zip(np.split(bins[keep], cuts), np.split(f_hz[keep], cuts), np.split(power[keep], cuts),
                         np.split(conf[keep], cuts)))
 

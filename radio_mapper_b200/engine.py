@@ -281,12 +281,13 @@ _pinned_peaks: dict = {}
 
 
 def find_peaks_batch(db: torch.Tensor, height: float, distance: int = 0, height_above_mean: bool = False, cap: int = 1024,
-                     flat: bool = False):
+                     flat: bool = False, gate_dc_bins: int = 0, gate_conf_min: float = 0.0):
     """scipy.signal.find_peaks(row, height=, distance=) for every row of db[n_rows, n] in one launch, plus each
     row's mean and median.  height_above_mean=True uses mean(row) + height (signal_analyzer.py:75).
     Returns (peaks: list of int32 arrays (ascending bins), heights: list of float32 arrays, mean[n_rows],
     median[n_rows]) on the host; only the peak lists cross PCIe, not the spectra.  flat=True returns
-    (bins, heights, offsets[n_rows + 1], mean, median) with row r in [offsets[r], offsets[r+1])."""
+    (bins, heights, offsets[n_rows + 1], mean, median) with row r in [offsets[r], offsets[r+1]).
+    gate_dc_bins / gate_conf_min apply the buoy detector's gates on the device (see include/rmx.h)."""
     _require_cuda(db, torch.float32, "db")
     if db.ndim != 2:
         raise ValueError("db must be [n_rows, n]")
@@ -301,8 +302,9 @@ def find_peaks_batch(db: torch.Tensor, height: float, distance: int = 0, height_
     stats = torch.empty((n_rows, 2), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _native.check(_lib.rmx_find_peaks_batch(_ptr(db), n_rows, n, db.stride(0), float(height), int(bool(height_above_mean)),
-                                                int(np.ceil(distance)) if distance else 0, _ptr(idx), _ptr(hts), _ptr(count),
-                                                cap, _ptr(stats), _stream_ptr()), "rmx_find_peaks_batch")
+                                                int(np.ceil(distance)) if distance else 0, int(gate_dc_bins), float(gate_conf_min),
+                                                _ptr(idx), _ptr(hts), _ptr(count), cap, _ptr(stats), _stream_ptr()),
+                      "rmx_find_peaks_batch")
     c = count.cpu().numpy()
     st = stats.cpu().numpy()
     most = int(min(cap, max(0, c.max(initial=0))))
@@ -342,6 +344,9 @@ def find_peaks_batch(db: torch.Tensor, height: float, distance: int = 0, height_
             cand = threshold_peaks(db[r], thr)
             row = db[r].cpu().numpy()
             kept = select_by_distance(cand, row[cand], distance) if distance else cand
+            if gate_dc_bins > 0 or gate_conf_min > 0:
+                conf = np.clip((row[kept] - np.float32(st[r, 1])).astype(np.float32) / np.float32(20.0), 0.0, 1.0)
+                kept = kept[(np.minimum(kept, n - kept) >= gate_dc_bins) & (conf >= np.float32(gate_conf_min))]
             peaks.append(kept.astype(np.int32)); heights.append(row[kept])
         else:
             peaks.append(idx_h[r, :c[r]].copy()); heights.append(hts_h[r, :c[r]].copy())
