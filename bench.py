@@ -420,10 +420,41 @@ def run_b200(args, wl):
         welch = {"workload": "2.4 Msps, 64k-bin Welch PSD, 1000 segments", "value": n_seg * nperseg / (wms * 1e-3),
                  "unit": "samples/s", "ms": wms, "passes": wplan.pass_lengths,
                  "hbm_frac": (2.0 * n_seg * nperseg + 4 * nperseg) / (wms * 1e-3) / 1e9 / peak,
-                 "note": "fp32-ALU bound (SURVEY §8d): 2 B/sample of traffic against ~80 flop/sample"}
+                 "kernel": "one thread-block-cluster kernel (8 CTAs hold a 64k segment in distributed shared memory)",
+                 "note": "fp32-ALU / DSMEM bound (SURVEY §8d): 2 B/sample of traffic against ~80 flop/sample"}
         del wiq, wplan
     except Exception as exc:  # secondary measurement: never fail the headline line
         welch = {"error": repr(exc)}
+
+    # ---- secondary: block detection (buoy_node.py:391-433) batched over raw cu8 blocks from pinned host memory ----
+    detect = None
+    try:
+        from radio_mapper_b200 import synth as _synth
+        from radio_mapper_b200.detectors import BuoySignalDetector
+        nblk, nlen = 256, 32768
+        ub, _ = _synth.welch_stream(9, nblk, nlen, fs)
+        blocks = torch.from_numpy(np.ascontiguousarray(ub.reshape(nblk, 2 * nlen))).pin_memory()
+        det = BuoySignalDetector("BUOY_B", 35.4676, -97.5164, fs)
+        det.detect_blocks_arrays(blocks, 100.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            res = det.detect_blocks_arrays(blocks, 100.0)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+        import oracle as _oracle
+        t0 = time.perf_counter()
+        for bq in range(4):
+            xo = _oracle.unpack_cu8(blocks[bq].numpy())
+            po = _oracle.spectrum_db(_oracle.forward_fft(xo))
+            oo = _oracle.score_peaks_buoy(po, _oracle.detect_peaks_fixed(po), _oracle.freq_axis_hz(nlen, fs, 100_000_000), 100_000_000)
+        dt_cpu = (time.perf_counter() - t0) / 4
+        detect = {"workload": "%d raw cu8 blocks x %d samples: unpack, FFT, dB, find_peaks(height=-70, distance=10), median, gates" % (nblk, nlen),
+                  "value": nblk / dt, "unit": "blocks/s", "ms_per_batch": 1e3 * dt, "h2d_bytes_per_batch": int(blocks.numel()),
+                  "cpu_oracle_blocks_per_s_1_thread": 1.0 / dt_cpu,
+                  "block3_detections_match_oracle": sorted(int(k) for k in res[3][0]) == sorted(int(o["index"]) for o in oo)}
+    except Exception as exc:
+        detect = {"error": repr(exc)}
 
     # ---- CPU baseline: the oracle on a bounded sample, this box's host cores ---------------------
     b = 4 if N <= (1 << 22) else 2
@@ -454,7 +485,7 @@ def run_b200(args, wl):
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "windowed_search": windowed,
-        "welch_psd": welch,
+        "welch_psd": welch, "block_detect": detect,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
