@@ -42,7 +42,7 @@
 #define RMX_PAIR_BULK_STORE 1   // row pass output through shared memory + cp.async.bulk (one row per tile)
 #endif
 #ifndef RMX_PAIR_TWTREE
-#define RMX_PAIR_TWTREE 1   // contiguous pair pass: build stage twiddles from their power-of-two entries
+#define RMX_PAIR_TWTREE 1   // row passes and forward column passes: build stage twiddles from their power-of-two entries
 #endif
 #ifndef RMX_PAIR_RUN_CTAS
 #define RMX_PAIR_RUN_CTAS 3   // resident CTAs per SM for the X_i-stationary pair pass
@@ -216,7 +216,7 @@ k_contig(const PassParams p) {
                 const float2 a = __ldg(xi + off + u * NT), b = __ldg(xj + off + u * NT);
                 r[u] = cmul_conj(b, a);
             }
-            fft_tile<GEO, true>(r, smem, g, i0, p.tabs);
+            fft_tile<GEO, true, (RMX_PAIR_TWTREE != 0)>(r, smem, g, i0, p.tabs);
             // twiddle of (row, lag): w_L^{+phi*lag} with lag = a*NT + i0  ->  A * B^a,
             // A = w^{phi*i0} (per thread), B = w^{phi*NT} (per row); exact roots, short product chains
             const uint32_t phi = row_frequency(p, row);
@@ -326,7 +326,7 @@ k_contig(const PassParams p) {
             }
         }
 
-        fft_tile<GEO, INV, (MODE == C_INV_PAIR && RMX_PAIR_TWTREE != 0)>(r, smem, g, i0, p.tabs);
+        fft_tile<GEO, INV, (RMX_PAIR_TWTREE != 0)>(r, smem, g, i0, p.tabs);
 
         if constexpr (MODE == C_INV_PAIR) {
             if (p.post_logm > 0) {
@@ -471,7 +471,8 @@ __global__ void __launch_bounds__(kThreads, (MODE == K_INV_ARGMAX_PRE && LOGE ==
         for (int u = 0; u < E; ++u) r[u] = cmul(r[u], tw[u]);
     }
 
-    fft_tile<GEO, INV>(r, smem, g, i0, p.tabs);
+    // (twiddle tree in the forward passes only: the inverse column kernels are register-tight)
+    fft_tile<GEO, INV, (!INV && RMX_PAIR_TWTREE != 0)>(r, smem, g, i0, p.tabs);
 
     if constexpr (!INV) {
         float2 tw[E];
@@ -802,7 +803,7 @@ __global__ void __launch_bounds__(kThreads, argmax_tma_ctas(LOGE)) k_col_argmax_
             for (int u = 0; u < E; ++u) r[u] = cmul(r[u], tw[u]);
         }
 
-        fft_tile<GEO, true, false>(r, smem, g, i0, p.tabs, [&]() {
+        fft_tile<GEO, true, false>(r, smem, g, i0, p.tabs, [&]() {      // no twiddle tree: 80 registers (measured +22 % with it)
             // every generic-proxy access to the buffer is ordered before the async-proxy refill
             fence_proxy_async();
             __syncthreads();
