@@ -114,6 +114,26 @@ def test_welch_cluster_kernel_matches_two_pass(rmx, monkeypatch, nperseg):
     assert np.max(np.abs(a / b - 1)) < 2e-5
 
 
+def test_cfg2_size_welch_against_oracle_and_parseval(rmx):
+    """BASELINE config 2 at full size: 1000 segments x 65536 bins (131 MB of cu8).  Against scipy.signal.welch
+    on the same bytes, and Parseval: the PSD integrates to the mean windowed power (size-independent)."""
+    nperseg, n_seg, fs = 65536, 1000, 2.4e6
+    iq, bins = synth.welch_stream(21, n_seg, nperseg, int(fs))
+    plan = rmx.Plan(n_seg, nperseg, nperseg)
+    psd = plan.welch_psd(_cuda(iq), fs).cpu().numpy()
+    x = oracle.unpack_cu8(iq)
+    _, ref = oracle.welch_psd(x, fs, nperseg)
+    assert np.max(np.abs(psd / ref - 1)) < 2e-5
+    w = scipy.signal.get_window("hann", nperseg).astype(np.float32)
+    seg = x.reshape(n_seg, nperseg)
+    mean_windowed_power = float(np.mean(np.sum((np.abs(seg) ** 2).astype(np.float64) * (w.astype(np.float64) ** 2), axis=1)))
+    integral = float(psd.astype(np.float64).sum()) * fs / nperseg * float(np.sum(w.astype(np.float64) ** 2))
+    assert abs(integral / mean_windowed_power - 1) < 1e-5
+    db = rmx.power_db(_cuda(psd)).cpu().numpy()
+    got = set(rmx.threshold_peaks(_cuda(db), float(np.mean(db) + 10)).tolist())
+    assert set(map(int, bins)).issubset(got)
+
+
 def test_welch_detect_finds_the_tones(rmx):
     from radio_mapper_b200.signal_analyzer import SignalAnalyzer
     nperseg, n_seg = 65536, 40
