@@ -754,6 +754,13 @@ __global__ void __launch_bounds__(kThreads, argmax_tma_ctas(LOGE)) k_col_argmax_
     constexpr uint32_t TILE_BYTES = (uint32_t)GEO::TILE * sizeof(float2);
     extern __shared__ float2 smem_raw[];
     __shared__ __align__(8) unsigned long long mbar;
+    __shared__ float s_am_v[2][kThreads / 32];
+    __shared__ unsigned s_am_rank[2];
+    int am_par = 0;
+    bool am_have = false;
+    float am_prev_val = -1.f;
+    long long am_prev_slot = 0;
+    if (threadIdx.x == 0) { s_am_rank[0] = 0xffffffffu; s_am_rank[1] = 0xffffffffu; }
     // 128-byte aligned TMA destination, kept in the shared address space (LDS/STS, not generic LD/ST)
     float2* smem = smem_raw + (((128u - (smem_u32(smem_raw) & 127u)) & 127u) >> 3);
 
@@ -835,20 +842,46 @@ __global__ void __launch_bounds__(kThreads, argmax_tma_ctas(LOGE)) k_col_argmax_
                 bv = fmaxf(bv, v[u]);
             }
         }
-        uint32_t brank;
-        block_argmax(bv, brank, [&](float target) {
-            uint32_t best = 0xffffffffu;
+        // Block arg-max with ONE barrier per tile: the per-warp maxima and the winning rank live in buffers
+        // indexed by tile parity, and thread 0 writes the partial of tile t after the barrier of tile t+1 (which
+        // every thread passes only after its atomicMin of tile t).
+        {
+            float m = bv;
 #pragma unroll
-            for (int u = 0; u < E; ++u)
-                if (v[u] == target) best = min(best, (rank0 + (uint32_t)u * rstep) & lmask);
-            return best;
-        });
-        if (threadIdx.x == 0) {
-            Partial out;
-            out.val = bv;
-            out.rank = brank;
-            p.partials[(item << log_tpb) + jt] = out;
+            for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+            if ((threadIdx.x & 31) == 0) s_am_v[am_par][threadIdx.x >> 5] = m;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (am_have) {                              // partial of the previous tile
+                    Partial out;
+                    out.val = am_prev_val;
+                    out.rank = s_am_rank[am_par ^ 1];
+                    p.partials[am_prev_slot] = out;
+                }
+                s_am_rank[am_par ^ 1] = 0xffffffffu;        // free for the tile after this one
+            }
+            float bm = s_am_v[am_par][0];
+#pragma unroll
+            for (int w = 1; w < kThreads / 32; ++w) bm = fmaxf(bm, s_am_v[am_par][w]);
+            if (bv == bm && bm >= 0.f) {
+                uint32_t best = 0xffffffffu;
+#pragma unroll
+                for (int u = 0; u < E; ++u)
+                    if (v[u] == bm) best = min(best, (rank0 + (uint32_t)u * rstep) & lmask);
+                atomicMin(&s_am_rank[am_par], best);
+            }
+            am_prev_val = bm;
+            am_prev_slot = (item << log_tpb) + jt;
+            am_have = true;
+            am_par ^= 1;
         }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && am_have) {
+        Partial out;
+        out.val = am_prev_val;
+        out.rank = s_am_rank[am_par ^ 1];
+        p.partials[am_prev_slot] = out;
     }
 }
 
