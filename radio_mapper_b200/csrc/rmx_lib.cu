@@ -1450,35 +1450,83 @@ __global__ void __launch_bounds__(1024) k_find_peaks_batch(const float* __restri
     }
     __syncthreads();
     // ---- (3) distance rule --------------------------------------------------------------------
+    // Sequential definition: visit candidates from the highest priority (height, then position) down; a kept one
+    // removes its not-yet-visited neighbours closer than `distance`.  Equivalent fixed point, evaluated in
+    // parallel: a candidate is REMOVED once some higher-priority neighbour within `distance` is KEPT, and KEPT once
+    // all of them are removed.  Rounds = longest chain of such dependencies (a handful on noise-like spectra);
+    // if 64 rounds do not settle everything, the remainder is finished in priority order by one thread.
     if (distance > 1 && n_cand > 1) {
-        // priority order = ascending (height, position): bitonic sort of the 64-bit composites
-        int m = 1;
-        while (m < n_cand) m <<= 1;
-        for (int k = n_cand + (int)threadIdx.x; k < m; k += blockDim.x) s_sort[k] = ~0ULL;
+        constexpr uint8_t REMOVED = 0, KEPT = 1, UNDECIDED = 2;
+        for (int k = threadIdx.x; k < n_cand; k += blockDim.x) s_keep[k] = UNDECIDED;
         __syncthreads();
-        for (int size = 2; size <= m; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
-                    const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
-                    const int j = i | stride;
-                    const bool up = (i & size) == 0;
-                    const unsigned long long a = s_sort[i], b = s_sort[j];
-                    if ((a > b) == up) { s_sort[i] = b; s_sort[j] = a; }
-                }
-                __syncthreads();
-            }
-        }
-        // visit from the highest priority down; a kept candidate removes its not-yet-visited neighbours
-        if (threadIdx.x == 0) {
-            for (int o = n_cand - 1; o >= 0; --o) {
-                const int j = (int)(unsigned)(s_sort[o] & 0xffffffffULL);
-                if (!s_keep[j]) continue;
+        auto higher = [&](int m, float hm, int j, float hj) { return hm > hj || (hm == hj && m > j); };
+        int rounds = 0;
+        bool pending = true;
+        while (pending && rounds < 64) {
+            int undecided = 0;
+            for (int j = threadIdx.x; j < n_cand; j += blockDim.x) {
+                if (s_keep[j] != UNDECIDED) continue;
                 const int pj = s_pos[j];
-                for (int k = j - 1; k >= 0 && pj - s_pos[k] < distance; --k) s_keep[k] = 0;
-                for (int k = j + 1; k < n_cand && s_pos[k] - pj < distance; ++k) s_keep[k] = 0;
+                const float hj = x[pj];
+                bool removed = false, waiting = false;
+                for (int m = j - 1; m >= 0 && pj - s_pos[m] < distance; --m) {
+                    if (!higher(m, x[s_pos[m]], j, hj)) continue;
+                    const uint8_t st = s_keep[m];
+                    removed |= st == KEPT;
+                    waiting |= st == UNDECIDED;
+                }
+                for (int m = j + 1; m < n_cand && s_pos[m] - pj < distance; ++m) {
+                    if (!higher(m, x[s_pos[m]], j, hj)) continue;
+                    const uint8_t st = s_keep[m];
+                    removed |= st == KEPT;
+                    waiting |= st == UNDECIDED;
+                }
+                if (removed) s_keep[j] = REMOVED;
+                else if (!waiting) s_keep[j] = KEPT;
+                else undecided = 1;
             }
+            pending = __syncthreads_or(undecided) != 0;
+            ++rounds;
         }
-        __syncthreads();
+        if (pending) {
+            // rare: long dependency chains (e.g. a monotone ramp of plateaus).  Sort the composites and let one
+            // thread finish the undecided candidates in priority order.
+            int m2 = 1;
+            while (m2 < n_cand) m2 <<= 1;
+            for (int k = threadIdx.x; k < m2; k += blockDim.x)
+                s_sort[k] = k < n_cand ? (((unsigned long long)float_order_key(x[s_pos[k]]) << 32) | (unsigned)k) : ~0ULL;
+            __syncthreads();
+            for (int size = 2; size <= m2; size <<= 1) {
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int t = threadIdx.x; t < (m2 >> 1); t += blockDim.x) {
+                        const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                        const int j = i | stride;
+                        const bool up = (i & size) == 0;
+                        const unsigned long long a = s_sort[i], b = s_sort[j];
+                        if ((a > b) == up) { s_sort[i] = b; s_sort[j] = a; }
+                    }
+                    __syncthreads();
+                }
+            }
+            if (threadIdx.x == 0) {
+                for (int o = n_cand - 1; o >= 0; --o) {
+                    const int j = (int)(unsigned)(s_sort[o] & 0xffffffffULL);
+                    if (s_keep[j] == REMOVED) continue;
+                    if (s_keep[j] == UNDECIDED) {
+                        // every higher-priority candidate is decided by now
+                        bool removed = false;
+                        const int pj = s_pos[j];
+                        const float hj = x[pj];
+                        for (int m = j - 1; m >= 0 && pj - s_pos[m] < distance; --m)
+                            removed |= s_keep[m] == KEPT && higher(m, x[s_pos[m]], j, hj);
+                        for (int m = j + 1; m < n_cand && s_pos[m] - pj < distance; ++m)
+                            removed |= s_keep[m] == KEPT && higher(m, x[s_pos[m]], j, hj);
+                        s_keep[j] = removed ? REMOVED : KEPT;
+                    }
+                }
+            }
+            __syncthreads();
+        }
     }
     // optional gates of the buoy detector (buoy_node.py:423-433), applied AFTER the distance rule like the
     // reference's loop over find_peaks' output: drop bins closer than gate_dc_bins to DC (|f - fc| < 10 kHz) and
