@@ -178,6 +178,12 @@ RMX_API int rmx_find_peaks_batch(const float* db, int n_rows, int n, size_t row_
                          int distance, int gate_dc_bins, float gate_conf_min, int32_t* idx, float* heights,
                          int32_t* count, int cap, float* stats, void* stream);
 
+/* Stage 5e batched — the -3 dB bandwidth walk of iq_stream_client.py:254-278 for the peaks rmx_find_peaks_batch
+ * returned: width[row][k] = right - left with left/right walked away from peak k while db > db[peak] - drop_db
+ * (stopping at bins 0 and n-1); bandwidth_hz = width * fs / n. */
+RMX_API int rmx_peak_bandwidth_batch(const float* db, int n_rows, int n, size_t row_stride, const int32_t* idx,
+                             const int32_t* count, int cap, float drop_db, int32_t* width, void* stream);
+
 /* Per-launch timing with CUDA events on the launching stream (off by default).  enable != 0 clears
  * earlier records and starts recording; collect synchronises the recorded events and returns the
  * number of distinct kernel names written to out[0..cap). */

@@ -43,6 +43,7 @@ SIGNATURES = {
     "rmx_select_by_distance_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "rmx_mean_median": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rmx_signal_stats": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
+    "rmx_peak_bandwidth_batch": (c_int, [c_void_p, c_int, c_int, c_size_t, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     "rmx_find_peaks_batch": (c_int, [c_void_p, c_int, c_int, c_size_t, c_float, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                      c_void_p, c_int, c_void_p, c_void_p]),
     "rmx_signal_energy": (c_int, [c_void_p, c_size_t, c_int, c_size_t, c_void_p, c_void_p]),

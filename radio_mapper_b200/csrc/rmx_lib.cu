@@ -1578,6 +1578,35 @@ extern "C" int rmx_find_peaks_batch(const float* db, int n_rows, int n, size_t r
     return RMX_OK;
 }
 
+// -3 dB bandwidth walk of iq_stream_client.py:254-278 for every peak of every row: one thread per peak.
+__global__ void __launch_bounds__(256) k_peak_bandwidth_batch(const float* __restrict__ db, int n, long long row_stride,
+                                                              const int32_t* __restrict__ idx, const int32_t* __restrict__ count,
+                                                              int cap, float drop_db, int32_t* __restrict__ width) {
+    const int row = blockIdx.y;
+    const int c = min(max(count[row], 0), cap);
+    const float* __restrict__ x = db + (long long)row * row_stride;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < c; k += gridDim.x * blockDim.x) {
+        const int peak = idx[(long long)row * cap + k];
+        const float thr = x[peak] - drop_db;
+        int left = peak, right = peak;
+        while (left > 0 && x[left] > thr) --left;
+        while (right < n - 1 && x[right] > thr) ++right;
+        width[(long long)row * cap + k] = right - left;
+    }
+}
+
+extern "C" int rmx_peak_bandwidth_batch(const float* db, int n_rows, int n, size_t row_stride, const int32_t* idx,
+                                        const int32_t* count, int cap, float drop_db, int32_t* width, void* stream) {
+    if (!db || !idx || !count || !width) return fail(RMX_ERR_ARG, "null argument to rmx_peak_bandwidth_batch");
+    if (n_rows <= 0) return RMX_OK;
+    if (n < 1 || cap < 1) return fail(RMX_ERR_ARG, "rmx_peak_bandwidth_batch needs n >= 1 and cap >= 1");
+    if (row_stride == 0) row_stride = (size_t)n;
+    k_peak_bandwidth_batch<<<dim3((unsigned)std::min(64, (cap + 255) / 256), (unsigned)n_rows), 256, 0, (cudaStream_t)stream>>>(
+        db, n, (long long)row_stride, idx, count, cap, drop_db, width);
+    LAUNCH_CHECK("peak_bandwidth_batch");
+    return RMX_OK;
+}
+
 // exact integer statistics: |x|^2 = ((2I-255)^2 + (2Q-255)^2) / 4
 __global__ void __launch_bounds__(256) k_signal_stats(const uint8_t* __restrict__ in, size_t n,
                                                       unsigned long long* __restrict__ acc) {

@@ -244,6 +244,35 @@ class StreamSignalDetector:
     def detect_signals(self, iq_samples: np.ndarray, center_freq_hz: float) -> List[StreamDetection]:
         return self.detect_signals_indexed(iq_samples, center_freq_hz)[1]
 
+    def detect_blocks_arrays(self, iq_u8, center_freq_hz: float):
+        """`detect_signals` for many raw cu8 blocks at once: iq_u8 is uint8[n_blocks, 2N] as read from the
+        rtl_sdr pipe (`read_iq_samples` unpacks exactly these bytes, :148-159), N a power of two >= 16.  Returns per
+        block (bins, frequency_hz, power_db, bandwidth_hz, confidence) arrays: FFT, dB, find_peaks(height=-70,
+        distance=10), median and the -3 dB bandwidth walk (:254-278) all run on the device."""
+        import torch
+        eng = _engine()
+        t = torch.as_tensor(iq_u8)
+        if t.ndim != 2 or t.dtype != torch.uint8 or t.shape[1] % 2:
+            raise ValueError("iq_u8 must be uint8[n_blocks, 2N]")
+        nb, n = t.shape[0], t.shape[1] // 2
+        if not (eng.is_pow2(n) and n >= 16):
+            raise ValueError("detect_blocks_arrays needs a power-of-two block length >= 16")
+        key = (nb, n, n)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = eng.Plan(nb, n, n)
+        db = plan.spectrum_db(plan.forward(t.cuda(non_blocking=True)))
+        bins, power, off, _, medians, width = eng.find_peaks_batch(db, self.detection_threshold, 10, cap=n // 10 + 2,
+                                                                   flat=True, bandwidth_drop_db=3.0)
+        abs_freqs = np.fft.fftfreq(n, 1.0 / self.sample_rate) + center_freq_hz
+        f_hz = abs_freqs[bins]
+        med = np.repeat(medians, np.diff(off))
+        conf = np.minimum((power - med) / np.float32(20.0), np.float32(1.0))          # :215-217, no lower clamp
+        bw = width * (self.sample_rate / n)
+        cuts = off[1:-1]
+        return list(zip(np.split(bins, cuts), np.split(f_hz, cuts), np.split(power, cuts), np.split(bw, cuts),
+                        np.split(conf, cuts)))
+
     def detect_signals_indexed(self, iq_samples: np.ndarray, center_freq_hz: float):
         """-> (FFT bin of each detection, detections)."""
         import torch

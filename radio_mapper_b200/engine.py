@@ -281,13 +281,15 @@ _pinned_peaks: dict = {}
 
 
 def find_peaks_batch(db: torch.Tensor, height: float, distance: int = 0, height_above_mean: bool = False, cap: int = 1024,
-                     flat: bool = False, gate_dc_bins: int = 0, gate_conf_min: float = 0.0):
+                     flat: bool = False, gate_dc_bins: int = 0, gate_conf_min: float = 0.0, bandwidth_drop_db: Optional[float] = None):
     """scipy.signal.find_peaks(row, height=, distance=) for every row of db[n_rows, n] in one launch, plus each
     row's mean and median.  height_above_mean=True uses mean(row) + height (signal_analyzer.py:75).
     Returns (peaks: list of int32 arrays (ascending bins), heights: list of float32 arrays, mean[n_rows],
     median[n_rows]) on the host; only the peak lists cross PCIe, not the spectra.  flat=True returns
     (bins, heights, offsets[n_rows + 1], mean, median) with row r in [offsets[r], offsets[r+1]).
-    gate_dc_bins / gate_conf_min apply the buoy detector's gates on the device (see include/rmx.h)."""
+    gate_dc_bins / gate_conf_min apply the buoy detector's gates on the device (see include/rmx.h).
+    bandwidth_drop_db (flat=True only) appends the per-peak width in bins of the -drop_db walk of
+    iq_stream_client.py:254-278 as a sixth return value."""
     _require_cuda(db, torch.float32, "db")
     if db.ndim != 2:
         raise ValueError("db must be [n_rows, n]")
@@ -305,6 +307,15 @@ def find_peaks_batch(db: torch.Tensor, height: float, distance: int = 0, height_
                                                 int(np.ceil(distance)) if distance else 0, int(gate_dc_bins), float(gate_conf_min),
                                                 _ptr(idx), _ptr(hts), _ptr(count), cap, _ptr(stats), _stream_ptr()),
                       "rmx_find_peaks_batch")
+    width = None
+    if bandwidth_drop_db is not None:
+        if not flat:
+            raise ValueError("bandwidth_drop_db needs flat=True")
+        width = torch.empty((n_rows, cap), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(_lib.rmx_peak_bandwidth_batch(_ptr(db), n_rows, n, db.stride(0), _ptr(idx), _ptr(count), cap,
+                                                        float(bandwidth_drop_db), _ptr(width), _stream_ptr()),
+                          "rmx_peak_bandwidth_batch")
     c = count.cpu().numpy()
     st = stats.cpu().numpy()
     most = int(min(cap, max(0, c.max(initial=0))))
@@ -334,6 +345,9 @@ def find_peaks_batch(db: torch.Tensor, height: float, distance: int = 0, height_
         if not ok.all():
             raise _native.RmxError("find_peaks_batch(flat=True): %d rows exceed the on-chip candidate limit or cap"
                                    % int((~ok).sum()))
+        if width is not None:
+            wid = width[:, :most].cpu().numpy()[mask] if most else np.empty(0, np.int32)
+            return flat_bins, flat_h, offsets, st[:, 0].copy(), st[:, 1].copy(), wid
         return flat_bins, flat_h, offsets, st[:, 0].copy(), st[:, 1].copy()
     peaks, heights = [], []
     for r in range(n_rows):

@@ -400,3 +400,22 @@ def test_correlate_iq_split_first_window_matches_device_path(n_buoys):
     pairs = [(i, j) for i in range(n_buoys) for j in range(i + 1, n_buoys)]
     for w in range(W):
         assert list(pinned["lag"][w]) == [int(delays[w, j] - delays[w, i]) for i, j in pairs]
+
+
+def test_stream_detect_blocks_arrays_equal_per_block():
+    """Batched stream detector (device bandwidth walk included) against detect_signals on each block."""
+    from radio_mapper_b200.detectors import StreamSignalDetector
+    nb, n = 6, 8192                                              # iq_stream_client.py:459 block size
+    u, _ = synth.welch_stream(31, nb, n)
+    blocks = u.reshape(nb, 2 * n)
+    det = StreamSignalDetector("NODE_T")
+    fc = 100.0e6
+    batched = det.detect_blocks_arrays(blocks, fc)
+    for b in range(nb):
+        bins, dets = det.detect_signals_indexed(oracle.unpack_cu8(blocks[b]), fc)
+        kb, f_hz, power, bw, conf = batched[b]
+        assert list(kb) == bins
+        assert np.array_equal(power, np.array([d.signal_strength_dbm for d in dets], np.float32))
+        assert np.array_equal(f_hz / 1e6, np.array([d.frequency_mhz for d in dets]))
+        assert np.array_equal(bw, np.array([d.bandwidth_hz for d in dets]))
+        assert np.allclose(conf, np.array([d.confidence for d in dets], np.float32), rtol=0, atol=1e-7)
