@@ -9,7 +9,7 @@ GPU arm: BuoySignalDetector.detect_blocks on a pinned host uint8[n_blocks, 2N] (
 find_peaks/median kernels, peak lists D2H, host scoring) and, for comparison, detect_block in a loop.
 CPU arm: the oracle (numpy/scipy, one thread) on a bounded sample of the same blocks.  One JSON line."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import oracle

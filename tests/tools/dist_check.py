@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """torchrun --nproc-per-node 2 tools/dist_check.py : the distributed=True API on real GPUs (NCCL)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch, torch.distributed as dist
 from radio_mapper_b200 import synth
 from radio_mapper_b200.tdoa_processor import TDOAProcessor

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Non-fail-fast numerical diagnostics of the CUDA path against the oracle (run on the GPU box)."""
 import sys, os, time, traceback
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import scipy.fft
 import torch

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Small, fast coverage of every kernel family for compute-sanitizer (memcheck / racecheck)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from radio_mapper_b200 import engine, synth, bluestein
 import oracle
