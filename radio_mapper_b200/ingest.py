@@ -160,6 +160,9 @@ class StreamingCorrelator:
         self._host = torch.empty((self.depth, B, BYTES_PER_SAMPLE * N), dtype=torch.uint8).pin_memory()
         self._dev = torch.empty((B, self.depth, BYTES_PER_SAMPLE * N), dtype=torch.uint8, device=self.device)
         self._copy_stream = torch.cuda.Stream(device=self.device)
+        # at most depth-1 windows are pending, so depth+1 result slots are never overwritten before they are read
+        self._rec_host = torch.empty((self.depth + 1, correlator.n_pairs, 4), dtype=torch.int32).pin_memory()
+        self._en_host = torch.empty((self.depth + 1, B), dtype=torch.int64).pin_memory()
         self.windows_done = 0
         self.h2d_bytes = 0
 
@@ -175,7 +178,7 @@ class StreamingCorrelator:
         slot_free = [None] * D          # event: the kernels that read device slot s have finished
         copied = [None] * D             # event: the H2D copy into device slot s has finished
         host_free = [None] * D          # event: the H2D copy out of host slot s has finished
-        pending: List = []              # (records_dev, energy_dev, done_event) in window order
+        pending: List = []              # (result slot, done_event) in window order
         with torch.cuda.device(self.device):
             compute = torch.cuda.current_stream()
             w = 0
@@ -200,20 +203,25 @@ class StreamingCorrelator:
                 self.h2d_bytes += view.numel()
                 compute.wait_event(copied[s])
                 rec, en = cor.run_device(self._dev, [s])
+                # results go to page-locked slots right behind this window's kernels, so handing a window back
+                # never waits for the kernels of the windows queued after it
+                r = w % (D + 1)
+                self._rec_host[r].copy_(rec[0], non_blocking=True)
+                self._en_host[r].copy_(en[0], non_blocking=True)
                 done = torch.cuda.Event()
                 done.record(compute)
                 slot_free[s] = done
-                pending.append((rec, en, done))
+                pending.append((r, done))
                 w += 1
                 # hand back every window whose kernels have already finished, keeping at most depth-1 in flight
-                while pending and (len(pending) >= D - 1 or pending[0][2].query()):
+                while pending and (len(pending) >= D - 1 or pending[0][1].query()):
                     yield self._finish(pending.pop(0))
             while pending:
                 yield self._finish(pending.pop(0))
 
     def _finish(self, item) -> np.ndarray:
-        rec, en, done = item
+        r, done = item
         done.synchronize()
-        out = self.cor._finish(rec.cpu().numpy(), en.cpu().numpy())[0]
+        out = self.cor._finish(self._rec_host[r].numpy()[None].copy(), self._en_host[r].numpy()[None].copy())[0]
         self.windows_done += 1
         return out
