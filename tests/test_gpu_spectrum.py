@@ -397,6 +397,13 @@ def test_correlate_iq_split_first_window_matches_device_path(n_buoys):
     device = proc.correlate_iq_records(iq.cuda())
     pageable = proc.correlate_iq_records(iq.numpy())
     assert pinned.tobytes() == device.tobytes() == pageable.tobytes()
+    # the lag-window (one-pass) search goes through the same grouping; its row chunks depend on the number of
+    # pairs per launch, so sums are re-associated: same lags, peaks / offsets within the north_star tolerances
+    win_p = proc.correlate_iq_records(iq.pin_memory(), max_lag=700)
+    win_d = proc.correlate_iq_records(iq.cuda(), max_lag=700)
+    assert np.array_equal(win_p["lag"], win_d["lag"]) and np.array_equal(win_p["lag"], pinned["lag"])
+    assert np.max(np.abs(win_p["peak"] / win_d["peak"] - 1)) <= 1e-4
+    assert np.max(np.abs(win_p["frac"] - win_d["frac"])) <= 1e-3
     pairs = [(i, j) for i in range(n_buoys) for j in range(i + 1, n_buoys)]
     for w in range(W):
         assert list(pinned["lag"][w]) == [int(delays[w, j] - delays[w, i]) for i, j in pairs]
