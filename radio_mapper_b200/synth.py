@@ -113,11 +113,13 @@ def welch_stream(seed, n_segments, nperseg, sample_rate=2_400_000, n_tones=5):
 
 
 def delayed_buoys_torch(seed, n_buoys, n_windows, n_samples, device, sample_rate=2_048_000,
-                        bandwidth_hz=200_000.0, snr_db=10.0, max_delay=342):
+                        bandwidth_hz=200_000.0, snr_db=10.0, max_delay=342, frac_delays=None):
     """GPU-side generator for full-size bench inputs (not bit-identical to `delayed_buoys`).
 
     Returns (iq_u8 CUDA uint8[B, W, 2N], delays int64[W, B]).  torch.fft is used here only to
     shape the synthetic source; it is data generation, not the product path.
+    frac_delays: optional per-buoy sub-sample delays in (-0.5, 0.5), applied to the band-limited source as a
+    phase ramp (buoy b hears the source delays[w, b] + frac_delays[b] samples late).
     """
     import torch
     g = torch.Generator(device=device)
@@ -134,9 +136,15 @@ def delayed_buoys_torch(seed, n_buoys, n_windows, n_samples, device, sample_rate
     for w in range(n_windows):
         spec = torch.randn(total, 2, generator=g, device=device)
         spec = torch.view_as_complex(spec) * keep
-        s = torch.fft.ifft(spec)
-        s = s / s.abs().pow(2).mean().sqrt()
+        s0 = torch.fft.ifft(spec)
+        norm = s0.abs().pow(2).mean().sqrt()
+        s = s0 / norm
         for b in range(n_buoys):
+            if frac_delays is not None and frac_delays[b] != 0.0:
+                ramp = torch.exp(-2j * torch.pi * (freqs / sample_rate) * float(frac_delays[b]))
+                s = torch.fft.ifft(spec * ramp) / norm
+            elif frac_delays is not None:
+                s = s0 / norm
             start = pad - int(delays_h[w, b])
             gain = 0.7 + 0.3 * float(torch.rand(1, generator=g, device=device))
             nz = torch.view_as_complex(torch.randn(n_samples, 2, generator=g, device=device)) * (noise_amp / 2.0 ** 0.5)

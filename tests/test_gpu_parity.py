@@ -347,3 +347,25 @@ def test_linearity_and_shift_properties(rmx):
     x = oracle.unpack_cu8(a).astype(np.complex128)
     e_spec = float((S[0].abs().double() ** 2).sum().item())
     assert abs(e_spec / (plan.fft_len * np.sum(np.abs(x) ** 2)) - 1) < 1e-5
+
+
+def test_subsample_delay_accuracy_vs_snr(rmx):
+    """BASELINE config 5's sweep at a test-sized window: known integer + fractional delays, per-buoy SNR from
+    +20 to -10 dB.  The measured delay (lag + parabolic offset) tracks the truth, and the error grows as the
+    SNR falls (`tests/tools/snr_sweep.py` runs the same sweep at 2^26 samples)."""
+    import torch
+    n, B = 1 << 20, 4
+    frac = np.array([0.0, 0.31, -0.22, 0.4])
+    plan = rmx.Plan(B, n)
+    pairs_h = rmx.pair_table(B)
+    pairs = _cuda(pairs_h)
+    rms = {}
+    for snr in (20, 0, -10):
+        iq, d = synth.delayed_buoys_torch(300 + snr, B, 1, n, torch.device("cuda"), snr_db=float(snr), frac_delays=frac)
+        rec = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(plan.forward(iq[:, 0, :]), pairs))
+        true = np.array([(d[0, j] + frac[j]) - (d[0, i] + frac[i]) for i, j in pairs_h])
+        err = (rec["lag"] + rec["frac"]) - true
+        rms[snr] = float(np.sqrt(np.mean(err ** 2)))
+        assert np.max(np.abs(err)) < 0.5                       # always within half a sample of the truth
+    assert rms[20] < 5e-3 and rms[0] < 5e-2 and rms[-10] < 0.3
+    assert rms[20] < rms[0] < rms[-10]
