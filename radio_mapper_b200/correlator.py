@@ -48,6 +48,8 @@ class Correlator:
         self._staging: Optional[torch.Tensor] = None
         self._copy_stream = None
         self._split = None           # plans / pair subsets of the split first window
+        self._tile_plans = {}        # forward plans per tile size (run_device_tile)
+        self._tile_dev = {}          # device copies of a tile's buoy list and local pair table
         self.launches = 0            # kernels launched by the last run()
 
     # -- device-resident core ---------------------------------------------------------------
@@ -72,6 +74,42 @@ class Correlator:
                           "rmx_signal_energy")
             self.plan.xcorr_pairs_peak(self.spectra, pairs, out=records[k], max_pairs_in_flight=self.workspace_pairs)
             self.launches += n_passes + 1 + n_passes + 1
+        return records, energy
+
+    def run_device_tile(self, iq_dev: torch.Tensor, windows, tile):
+        """Pair-tiled form of run_device (sharding.tile_pairs): only the buoys of `tile` are transformed and only
+        its pairs correlated.  Returns (records int32[len(windows), P_tile, 4], energy int64[len(windows), B] of
+        ALL buoys -- the energy pass reads 2 bytes per sample and is not worth sharding)."""
+        cached = self._tile_dev.get(id(tile))
+        if cached is None:
+            cached = self._tile_dev[id(tile)] = (torch.from_numpy(tile["buoys"]).to(self.device),
+                                                 torch.from_numpy(np.ascontiguousarray(tile["local_pairs"])).to(self.device))
+        buoys, pairs_local = cached
+        nb = int(buoys.numel())
+        nw = len(windows)
+        n_local = int(tile["local_pairs"].shape[0])
+        records = torch.empty((nw, n_local, 4), dtype=torch.int32, device=self.device)
+        energy = torch.empty((nw, self.n_buoys), dtype=torch.int64, device=self.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if nb:
+            key = ("tile", nb)
+            sub_plan = self._tile_plans.get(key)
+            if sub_plan is None:
+                sub_plan = self._tile_plans[key] = engine.Plan(nb, self.n_samples, device=self.device)
+        n_passes = len(self.plan.pass_lengths)
+        for k, w in enumerate(windows):
+            view = iq_dev[:, w, :]
+            _native.check(_lib.rmx_signal_energy(ctypes.c_void_p(view.data_ptr()), view.stride(0) if self.n_buoys > 1 else 0,
+                                                 self.n_buoys, self.n_samples, ctypes.c_void_p(energy[k].data_ptr()), stream),
+                          "rmx_signal_energy")
+            self.launches += 1
+            if nb == 0 or n_local == 0:
+                continue
+            sub = view.index_select(0, buoys)                       # [nb, 2N] contiguous copy of this tile's rows
+            sub_plan.forward(sub, out=self.spectra[:nb])
+            self.plan.xcorr_pairs_peak(self.spectra[:nb], pairs_local, out=records[k],
+                                       max_pairs_in_flight=self.workspace_pairs)
+            self.launches += n_passes + n_passes + 1
         return records, energy
 
     # -- host-facing call ---------------------------------------------------------------------

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 from typing import List, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -68,3 +69,98 @@ def gather_records(rec: torch.Tensor, energy: torch.Tensor, n_windows: int, n_pa
     dist.all_gather(recs, pad_rec)
     full_rec = torch.cat([recs[r][:, : b - a] for r, (a, b) in enumerate(sizes)], dim=1)
     return full_rec, energy          # every rank computed all energies of its windows
+
+
+# ---------------------------------------------------------------------------------------------
+# tiled pair sharding: blocks of the upper-triangular pair matrix per rank, so a rank
+# transforms only the buoys its blocks touch instead of all of them
+# ---------------------------------------------------------------------------------------------
+FWD_COST_IN_PAIRS = 1.4     # forward FFT of one buoy ~ 1.4 pair correlations (B200, N = 2^20: 12.5 us vs 9.1 us)
+
+
+def _pair_index(i: int, j: int, n: int) -> int:
+    """Position of (i, j), i < j, in the i-major list `engine.pair_table(n)`."""
+    return i * n - i * (i + 1) // 2 + (j - i - 1)
+
+
+def tile_pairs(n_buoys: int, world: int):
+    """Deal the i<j pairs to `world` ranks as blocks of a k x k grouping of the buoys.
+
+    Returns a list (one entry per rank) of dicts:
+        buoys          sorted int64 array of the buoys the rank has to transform
+        local_pairs    int32[P_r, 2]: (i, j) as indices into `buoys`
+        global_index   int64[P_r]: position of each pair in the full i-major pair list
+    Every pair appears on exactly one rank.  The number of groups k and the block-to-rank assignment minimise
+    the most loaded rank's cost = pairs + FWD_COST_IN_PAIRS * buoys (longest-processing-time greedy); the result
+    depends only on (n_buoys, world), so every rank computes the same table."""
+    if world <= 1:
+        idx = np.arange(n_buoys * (n_buoys - 1) // 2, dtype=np.int64)
+        pairs = np.array([(i, j) for i in range(n_buoys) for j in range(i + 1, n_buoys)], dtype=np.int32).reshape(-1, 2)
+        return [dict(buoys=np.arange(n_buoys, dtype=np.int64), local_pairs=pairs, global_index=idx)]
+    best = None
+    for k in range(1, min(n_buoys, 4 * world) + 1):
+        if k * (k + 1) // 2 < world and k < n_buoys:
+            continue
+        bounds = [split_even(n_buoys, k, g) for g in range(k)]
+        blocks = []
+        for a in range(k):
+            for b in range(a, k):
+                na, nb = bounds[a][1] - bounds[a][0], bounds[b][1] - bounds[b][0]
+                cnt = na * (na - 1) // 2 if a == b else na * nb
+                if cnt:
+                    blocks.append((cnt, a, b))
+        blocks.sort(key=lambda t: (-t[0], t[1], t[2]))
+        groups = [set() for _ in range(world)]
+        npairs = [0] * world
+        owner = []
+        for cnt, a, b in blocks:
+            def cost(r):
+                g = groups[r] | {a, b}
+                return npairs[r] + cnt + FWD_COST_IN_PAIRS * sum(bounds[x][1] - bounds[x][0] for x in g)
+            r = min(range(world), key=lambda q: (cost(q), q))
+            groups[r] |= {a, b}
+            npairs[r] += cnt
+            owner.append(r)
+        worst = max(npairs[r] + FWD_COST_IN_PAIRS * sum(bounds[x][1] - bounds[x][0] for x in groups[r]) for r in range(world))
+        if best is None or worst < best[0]:
+            best = (worst, bounds, blocks, owner)
+    _, bounds, blocks, owner = best
+    out = []
+    for r in range(world):
+        mine = [(a, b) for (cnt, a, b), o in zip(blocks, owner) if o == r]
+        buoys = sorted({x for a, b in mine for g in (a, b) for x in range(bounds[g][0], bounds[g][1])})
+        pos = {x: t for t, x in enumerate(buoys)}
+        lp, gi = [], []
+        for a, b in sorted(mine):
+            for i in range(bounds[a][0], bounds[a][1]):
+                for j in range(bounds[b][0], bounds[b][1]):
+                    if i < j:
+                        lp.append((pos[i], pos[j]))
+                        gi.append(_pair_index(i, j, n_buoys))
+        out.append(dict(buoys=np.array(buoys, dtype=np.int64), local_pairs=np.array(lp, dtype=np.int32).reshape(-1, 2),
+                        global_index=np.array(gi, dtype=np.int64)))
+    return out
+
+
+_gather_perm_cache: dict = {}
+
+
+def gather_tiled_records(rec: torch.Tensor, tiles, n_pairs: int, world: int):
+    """rec: this rank's [W, P_r, 4] int32 records for its tile.  Returns [W, n_pairs, 4] in the i-major pair
+    order on every rank: one padded all_gather into a single buffer, then one index_select with a cached
+    permutation (the index lists are known to every rank)."""
+    width = max(len(t["global_index"]) for t in tiles)
+    key = (id(tiles), str(rec.device), width)
+    perm = _gather_perm_cache.get(key)
+    if perm is None:
+        src = np.empty(n_pairs, dtype=np.int64)                 # position of pair g in the concatenated padded buffers
+        for r, t in enumerate(tiles):
+            src[t["global_index"]] = r * width + np.arange(len(t["global_index"]))
+        perm = _gather_perm_cache[key] = torch.from_numpy(src).to(rec.device)
+    pad = rec.new_zeros((rec.shape[0], width, rec.shape[2]))
+    pad[:, : rec.shape[1]] = rec
+    buf = rec.new_empty((world, rec.shape[0], width, rec.shape[2]))
+    dist.all_gather_into_tensor(buf, pad) if hasattr(dist, "all_gather_into_tensor") and rec.is_cuda else \
+        dist.all_gather(list(buf.unbind(0)), pad)
+    cat = buf.permute(1, 0, 2, 3).reshape(rec.shape[0], world * width, rec.shape[2])
+    return cat.index_select(1, perm)

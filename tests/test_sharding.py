@@ -85,3 +85,50 @@ def test_gather_records_by_window_gloo():
 def test_gather_records_by_pair_gloo():
     out = _run(n_windows=1, n_pairs=7)
     assert [(r, a, b) for r, a, b, _ in out] == [(0, True, True), (1, True, True)]
+
+
+def test_tile_pairs_partition_and_buoy_sets():
+    """Blocks of the pair matrix: every pair on exactly one rank, local indices consistent with the rank's buoy
+    list, and at 64 buoys / 8 ranks each rank transforms half of the buoys for ~1/8 of the pairs."""
+    for n_buoys, world in [(64, 8), (64, 4), (64, 2), (64, 1), (16, 8), (16, 3), (5, 8), (3, 2), (2, 2)]:
+        tiles = sharding.tile_pairs(n_buoys, world)
+        assert len(tiles) == world
+        full = [(i, j) for i in range(n_buoys) for j in range(i + 1, n_buoys)]
+        seen = np.concatenate([t["global_index"] for t in tiles]) if full else np.empty(0, np.int64)
+        assert sorted(seen.tolist()) == list(range(len(full)))
+        for t in tiles:
+            assert t["local_pairs"].shape == (len(t["global_index"]), 2)
+            for (li, lj), g in zip(t["local_pairs"], t["global_index"]):
+                assert (int(t["buoys"][li]), int(t["buoys"][lj])) == full[int(g)]
+    tiles = sharding.tile_pairs(64, 8)
+    assert max(len(t["buoys"]) for t in tiles) == 32
+    assert max(len(t["global_index"]) for t in tiles) <= 256 and min(len(t["global_index"]) for t in tiles) >= 240
+
+
+def _tile_worker(rank, world, port, n_buoys, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_pairs = n_buoys * (n_buoys - 1) // 2
+        full = torch.arange(2 * n_pairs * 4, dtype=torch.int32).reshape(2, n_pairs, 4)
+        tiles = sharding.tile_pairs(n_buoys, world)
+        mine = full[:, torch.from_numpy(tiles[rank]["global_index"])].contiguous()
+        got = sharding.gather_tiled_records(mine, tiles, n_pairs, world)
+        q.put((rank, bool(torch.equal(got, full))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_tiled_records_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tile_worker, args=(r, 2, port, 9, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out == [(0, True), (1, True)]

@@ -16,8 +16,10 @@ import torch.distributed as dist
 from radio_mapper_b200 import sharding, synth
 from radio_mapper_b200.correlator import Correlator
 
-steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
-warmup = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+tiled = "--tiled" in sys.argv          # blocks of the pair matrix per rank instead of contiguous slices of the pair list
+steps = int(args[0]) if len(args) > 0 else 10
+warmup = int(args[1]) if len(args) > 1 else 3
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -30,9 +32,13 @@ iq, delays = synth.delayed_buoys_torch(4000, B, 1, N, dev)         # the same wi
 cor = Correlator(B, N, device=dev)
 P = cor.n_pairs
 windows, pair_slice = sharding.shard_units(1, P, world, rank)
+tiles = sharding.tile_pairs(B, world) if tiled else None
 
 
 def step():
+    if tiled:
+        rec, en = cor.run_device_tile(iq, windows, tiles[rank])
+        return sharding.gather_tiled_records(rec, tiles, P, world) if world > 1 else rec
     rec, en = cor.run_device(iq, windows, pair_slice)
     if world > 1:
         rec, en = sharding.gather_records(rec, en, 1, P, world, rank)
@@ -61,11 +67,15 @@ if world > 1:
     ms = float(t.item())
 if rank == 0:
     a, b = (0, P) if pair_slice is None else (pair_slice.start, pair_slice.stop)
+    if tiled:
+        a, b = 0, len(tiles[0]["global_index"])
     print(json.dumps({"metric": "correlated_pair_samples_per_sec", "value": P * N * steps / (ms * 1e-3), "unit": "pair-samples/s",
                       "n_gpus": world, "steps": steps, "ms_per_step": ms / steps, "scaling": "strong",
                       "config": {"workload": "cfg4 pair-sharded", "buoys": B, "pairs": P, "pairs_on_rank0": b - a,
                                  "samples_per_window": N, "passes": cor.plan.pass_lengths,
-                                 "sharding": "contiguous slices of the i<j pair list; every rank recomputes the 64 forward FFTs; "
+                                 "sharding": ("blocks of the upper-triangular pair matrix (sharding.tile_pairs): rank 0 transforms %d of the "
+                                              "%d buoys; NCCL all_gather of the 16-byte peak records" % (len(tiles[0]["buoys"]), B)) if tiled else
+                                             "contiguous slices of the i<j pair list; every rank recomputes the 64 forward FFTs; "
                                              "NCCL all_gather of the 16-byte peak records"},
                       "lags_match_known_delays": True}))
 if world > 1:
