@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RMX_VERSION 100
+#define RMX_VERSION 200
 
 #if defined(__GNUC__)
 #define RMX_API __attribute__((visibility("default")))
@@ -71,8 +71,21 @@ RMX_API int rmx_version(void);
 RMX_API int rmx_unpack_cu8(const uint8_t* in, rmx_complex64* out, size_t n_samples, void* stream);
 
 /* Plan: n_signals signals of n_samples complex samples each, zero-padded to fft_len (a power of
- * two >= 16, >= n_samples).  flags: reserved (0). */
+ * two >= 16, >= n_samples).  flags: 0 for the defaults, or an OR of the developer switches below — fixed for
+ * the life of the plan, so a process A/Bs kernel variants by creating two plans (nothing on the launch path
+ * reads the environment). */
+#define RMX_PLAN_TWIDDLE_IN_COL   0x01u  /* inter-pass twiddles on the input of the column pass, not the row pass output */
+#define RMX_PLAN_NO_TMA           0x02u  /* arg-max pass through per-thread strided loads instead of the TMA-fed kernel */
+#define RMX_PLAN_NO_PAIR_RUN      0x04u  /* one pair per CTA in the 4096-point row pass (no X_i-stationary walk) */
+#define RMX_PLAN_NO_WELCH_CLUSTER 0x08u  /* Welch PSD through the two-pass path even where the cluster kernel applies */
+#define RMX_PLAN_ROW_LOGN(n)      (((unsigned)(n) & 0x1fu) << 8)  /* force log2 of the row length of multi-pass plans */
 RMX_API int rmx_plan_create(rmx_plan** plan, int n_signals, size_t n_samples, size_t fft_len, unsigned flags);
+/* Tuning knobs (defaults are the measured best on B200): "pair_run" = 8 | 16 pairs walked by one CTA of the
+ * X_i-stationary row pass; "pair_prefetch" = 0 | 1 next X_j row by bulk copy into shared memory;
+ * "fwd_group_bytes" = forward passes run over groups of signals whose spectra fit this many bytes, so a pass
+ * reads the previous one's output from L2 (0 = all signals per launch); "welch_clusters" = resident clusters of
+ * the Welch kernel (0 = occupancy query). */
+RMX_API int rmx_plan_set_option(rmx_plan* plan, const char* name, long long value);
 RMX_API int rmx_plan_destroy(rmx_plan* plan);
 /* number of passes and their lengths n_t (outermost first); returns n_passes */
 RMX_API int rmx_plan_layout(const rmx_plan* plan, int32_t* pass_lengths, int cap);
@@ -144,6 +157,9 @@ RMX_API int rmx_spectrum_db(const rmx_plan* plan, const rmx_complex64* spectra, 
 RMX_API int rmx_welch_psd(rmx_plan* plan, const uint8_t* iq, float* psd, double sample_rate,
                   void* workspace, size_t workspace_bytes, void* stream);
 RMX_API size_t rmx_welch_workspace_bytes(const rmx_plan* plan, int segments_in_flight);
+/* which path rmx_welch_psd takes for this plan and input pointer: 1 = one cluster kernel (no spectra workspace),
+ * 0 = two passes (size the workspace for as many segments in flight as memory allows) */
+RMX_API int rmx_welch_path(const rmx_plan* plan, const uint8_t* iq);
 
 /* out[k] = 10*log10(in[k] + eps) */
 RMX_API int rmx_power_db(const float* in, float* out, size_t n, float eps, void* stream);

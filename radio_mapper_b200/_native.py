@@ -20,6 +20,8 @@ SIGNATURES = {
     "rmx_unpack_cu8": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "rmx_plan_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_size_t, c_size_t, c_uint]),
     "rmx_plan_destroy": (c_int, [c_void_p]),
+    "rmx_plan_set_option": (c_int, [c_void_p, ctypes.c_char_p, c_longlong]),
+    "rmx_welch_path": (c_int, [c_void_p, c_void_p]),
     "rmx_plan_layout": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_int32), c_int]),
     "rmx_plan_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "rmx_plan_set_max_lag": (c_int, [c_void_p, c_longlong]),
@@ -48,6 +50,31 @@ SIGNATURES = {
                                      c_void_p, c_int, c_void_p, c_void_p]),
     "rmx_signal_energy": (c_int, [c_void_p, c_size_t, c_int, c_size_t, c_void_p, c_void_p]),
 }
+
+# plan flags (include/rmx.h)
+PLAN_TWIDDLE_IN_COL, PLAN_NO_TMA, PLAN_NO_PAIR_RUN, PLAN_NO_WELCH_CLUSTER = 0x01, 0x02, 0x04, 0x08
+
+
+def plan_row_logn(n: int) -> int:
+    return (int(n) & 0x1F) << 8
+
+
+def flags_from_env() -> int:
+    """Developer switches: the RMX_* environment variables are read HERE, once per plan creation on the Python
+    side, and handed to rmx_plan_create as flags; the library itself never reads the environment."""
+    f = 0
+    if os.environ.get("RMX_TWIDDLE_IN_COL"):
+        f |= PLAN_TWIDDLE_IN_COL
+    if os.environ.get("RMX_NO_TMA"):
+        f |= PLAN_NO_TMA
+    if os.environ.get("RMX_NO_PAIR_RUN"):
+        f |= PLAN_NO_PAIR_RUN
+    if os.environ.get("RMX_NO_WELCH_CLUSTER"):
+        f |= PLAN_NO_WELCH_CLUSTER
+    if os.environ.get("RMX_CONTIG_LOGN"):
+        f |= plan_row_logn(int(os.environ["RMX_CONTIG_LOGN"]))
+    return f
+
 
 _lib = None
 

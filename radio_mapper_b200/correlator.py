@@ -33,8 +33,15 @@ def as_u8_tensor(iq_u8) -> torch.Tensor:
     return iq_u8
 
 
+WORKSPACE_FRACTION = 0.5      # default cap of the correlation workspace: this share of the free device memory
+STAGING_WINDOWS = 4           # host -> device staging ring (windows); copies run this far ahead of the kernels
+
+
 class Correlator:
     def __init__(self, n_buoys: int, n_samples: int, device=None, workspace_pairs: Optional[int] = None):
+        """workspace_pairs: pairs correlated per chunk (8*fft_len bytes of workspace each).  Default: all pairs if
+        they fit WORKSPACE_FRACTION of the free device memory, else as many as do (64 buoys at N = 2^22 would
+        otherwise ask for 135 GB); librmx walks the pair list in chunks of that size."""
         if n_buoys < 2:
             raise ValueError("need at least two buoys to correlate")
         self.n_buoys, self.n_samples = int(n_buoys), int(n_samples)
@@ -44,12 +51,19 @@ class Correlator:
         self.pairs = torch.from_numpy(self.pairs_host).to(self.device)
         self.n_pairs = len(self.pairs_host)
         self.spectra = torch.empty((self.n_buoys, self.plan.fft_len), dtype=torch.complex64, device=self.device)
+        if workspace_pairs is None:
+            per_pair = max(1, self.plan.workspace_bytes(1))
+            with torch.cuda.device(self.device):
+                free, _total = torch.cuda.mem_get_info()
+            fit = int(free * WORKSPACE_FRACTION) // per_pair
+            if fit < self.n_pairs:
+                workspace_pairs = max(1, fit)
         self.workspace_pairs = workspace_pairs
         self._staging: Optional[torch.Tensor] = None
         self._copy_stream = None
         self._split = None           # plans / pair subsets of the split first window
         self._tile_plans = {}        # forward plans per tile size (run_device_tile)
-        self._tile_dev = {}          # device copies of a tile's buoy list and local pair table
+        self._tile_dev = {}          # device copies of a tile's buoy list and local pair table, keyed by CONTENT
         self.launches = 0            # kernels launched by the last run()
 
     # -- device-resident core ---------------------------------------------------------------
@@ -80,10 +94,15 @@ class Correlator:
         """Pair-tiled form of run_device (sharding.tile_pairs): only the buoys of `tile` are transformed and only
         its pairs correlated.  Returns (records int32[len(windows), P_tile, 4], energy int64[len(windows), B] of
         ALL buoys -- the energy pass reads 2 bytes per sample and is not worth sharding)."""
-        cached = self._tile_dev.get(id(tile))
+        # content key (ids are reused after garbage collection): the tile's own key when it came from
+        # sharding.tiles_for, else its bytes
+        key = tile.get("key") or (tile["buoys"].tobytes(), np.ascontiguousarray(tile["local_pairs"]).tobytes())
+        cached = self._tile_dev.get(key)
         if cached is None:
-            cached = self._tile_dev[id(tile)] = (torch.from_numpy(tile["buoys"]).to(self.device),
-                                                 torch.from_numpy(np.ascontiguousarray(tile["local_pairs"])).to(self.device))
+            if len(self._tile_dev) >= 64:
+                self._tile_dev.clear()
+            cached = self._tile_dev[key] = (torch.from_numpy(tile["buoys"]).to(self.device),
+                                            torch.from_numpy(np.ascontiguousarray(tile["local_pairs"])).to(self.device))
         buoys, pairs_local = cached
         nb = int(buoys.numel())
         nw = len(windows)
@@ -123,54 +142,86 @@ class Correlator:
             self.plan.set_max_lag(max_lag)
         self.launches = 0
         world, rank = sharding.world_and_rank() if distributed else (1, 0)
-        windows, pair_slice = sharding.shard_units(n_windows, self.n_pairs, world, rank)
         with torch.cuda.device(self.device):
-            if iq_u8.is_cuda:
-                rec_dev, en_dev = self.run_device(iq_u8, windows, pair_slice)
+            if world > 1 and n_windows < world:
+                # fewer windows than ranks: blocks of the pair matrix per rank -- a rank transforms
+                # only the buoys its blocks touch and one all-gather assembles the records
+                tiles = sharding.tiles_for(self.n_buoys, world)
+                windows = list(range(n_windows))
+                if iq_u8.is_cuda:
+                    rec_dev, en_dev = self.run_device_tile(iq_u8, windows, tiles[rank])
+                else:
+                    rec_dev, en_dev = self._run_from_host(iq_u8, windows, None, tile=tiles[rank])
+                rec_dev = sharding.gather_tiled_records(rec_dev, tiles, self.n_pairs, world)
             else:
-                rec_dev, en_dev = self._run_from_host(iq_u8, windows, pair_slice)
-            if world > 1:
-                rec_dev, en_dev = sharding.gather_records(rec_dev, en_dev, n_windows, self.n_pairs, world, rank)
+                windows, pair_slice = sharding.shard_units(n_windows, self.n_pairs, world, rank)
+                if iq_u8.is_cuda:
+                    rec_dev, en_dev = self.run_device(iq_u8, windows, pair_slice)
+                else:
+                    rec_dev, en_dev = self._run_from_host(iq_u8, windows, pair_slice)
+                if world > 1:
+                    rec_dev, en_dev = sharding.gather_records(rec_dev, en_dev, n_windows, self.n_pairs, world, rank)
             rec = rec_dev.cpu().numpy()
             en = en_dev.cpu().numpy()
         return self._finish(rec, en)
 
-    def _run_from_host(self, iq_u8: torch.Tensor, windows, pair_slice):
+    def _run_from_host(self, iq_u8: torch.Tensor, windows, pair_slice, tile=None):
         """Host cu8 -> device, one window at a time on a copy stream, so the H2D transfer of window
         w+1 overlaps the FFT / correlate kernels of window w (pinned host memory makes the copies
-        asynchronous; pageable memory still works, just without overlap)."""
-        if self._staging is None or self._staging.shape != iq_u8.shape:
-            self._staging = torch.empty(iq_u8.shape, dtype=torch.uint8, device=self.device)
+        asynchronous; pageable memory still works, just without overlap).  Only THIS rank's windows are staged,
+        through a ring of STAGING_WINDOWS device slots (slot reuse waits for the kernels that read it)."""
+        depth = max(1, min(len(windows), STAGING_WINDOWS))
+        shape = (self.n_buoys, depth, 2 * self.n_samples)
+        if self._staging is None or tuple(self._staging.shape) != shape:
+            self._staging = None
+            self._staging = torch.empty(shape, dtype=torch.uint8, device=self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         compute = torch.cuda.current_stream()
         pairs = self.pairs if pair_slice is None else self.pairs[pair_slice].contiguous()
-        records = torch.empty((len(windows), pairs.shape[0], 4), dtype=torch.int32, device=self.device)
+        n_rec = pairs.shape[0] if tile is None else int(tile["local_pairs"].shape[0])
+        records = torch.empty((len(windows), n_rec, 4), dtype=torch.int32, device=self.device)
         energy = torch.empty((len(windows), self.n_buoys), dtype=torch.int64, device=self.device)
         self._copy_stream.wait_stream(compute)              # staging may still be read by earlier kernels
         # The first window has nothing to hide its copy behind, so it is cut into growing groups of buoys
         # (2, 2, 4, 8, ...): each group is transformed, and correlated with everything already on the device,
         # while the next group is still on the bus.
-        split = pair_slice is None and self.n_buoys >= 4 and len(windows) > 0 and iq_u8.is_pinned()
+        split = tile is None and pair_slice is None and self.n_buoys >= 4 and len(windows) > 0 and iq_u8.is_pinned()
         cuts = self._split_cuts() if split else []
-        events, cut_events = [], []
-        with torch.cuda.stream(self._copy_stream):
-            for k, w in enumerate(windows):
+
+        def copy_window(k):
+            """enqueue the copy of windows[k] into slot k % depth; returns (event, cut events)"""
+            cut_events = []
+            with torch.cuda.stream(self._copy_stream):
                 for b in range(self.n_buoys):               # contiguous rows: plain async memcpys
-                    self._staging[b, w].copy_(iq_u8[b, w], non_blocking=True)
+                    self._staging[b, k % depth].copy_(iq_u8[b, windows[k]], non_blocking=True)
                     if split and k == 0 and (b + 1) in cuts:
                         ev = torch.cuda.Event()
                         ev.record(self._copy_stream)
                         cut_events.append(ev)
                 ev = torch.cuda.Event()
                 ev.record(self._copy_stream)
-                events.append(ev)
-        for k, w in enumerate(windows):
+            return ev, cut_events
+
+        pending = {}
+        for k in range(min(depth, len(windows))):
+            pending[k] = copy_window(k)
+        for k in range(len(windows)):
+            ev, cut_events = pending.pop(k)
+            slot = k % depth
             if split and k == 0:
-                self._run_split_window(w, cuts, cut_events, records[0], energy[0])
-                continue
-            compute.wait_event(events[k])
-            self.run_device(self._staging, [w], pair_slice, records=records[k:k + 1], energy=energy[k:k + 1], pairs=pairs)
+                self._run_split_window(slot, cuts, cut_events, records[0], energy[0])
+            else:
+                compute.wait_event(ev)
+                if tile is not None:
+                    rec_k, en_k = self.run_device_tile(self._staging, [slot], tile)
+                    records[k].copy_(rec_k[0])
+                    energy[k].copy_(en_k[0])
+                else:
+                    self.run_device(self._staging, [slot], pair_slice, records=records[k:k + 1], energy=energy[k:k + 1], pairs=pairs)
+            if k + depth < len(windows):
+                self._copy_stream.wait_stream(compute)      # the slot is free once this window's kernels are done
+                pending[k + depth] = copy_window(k + depth)
         return records, energy
 
     def _split_cuts(self):

@@ -29,7 +29,7 @@ struct PairRunEntry {
     size_t smem_bytes;
     int run;
 };
-PairRunEntry get_pair_run_kernel(int logn, int loge);
+PairRunEntry get_pair_run_kernel(int logn, int loge, int run, bool prefetch);
 
 typedef void (*WelchClusterKernel)(const WelchClusterParams);
 struct WelchClusterEntry {

@@ -42,13 +42,19 @@ KernelEntry get_contig_kernel(int logn, int loge, int mode) {
     }
 }
 
-#ifndef RMX_PAIR_RUN
-#define RMX_PAIR_RUN 8
-#endif
-PairRunEntry get_pair_run_kernel(int logn, int loge) {
+template <int RUN, bool PREFETCH>
+static PairRunEntry pair_run_entry() {
+    using GEO = TileGeom<12, 4, false>;
+    const size_t exchange = size_t((GEO::NP + 15) & ~15) * sizeof(float2);
+    return PairRunEntry{(PassKernel)k_contig_pair_run<12, 4, RUN, PREFETCH>,
+                        PREFETCH ? exchange + size_t(GEO::N) * sizeof(float2) : GEO::SMEM_BYTES, RUN};
+}
+
+// run: pairs walked by one CTA (8 or 16); prefetch: next X_j row through a bulk copy into shared memory
+PairRunEntry get_pair_run_kernel(int logn, int loge, int run, bool prefetch) {
     if (logn == 12 && loge == 4) {
-        using GEO = TileGeom<12, 4, false>;
-        return PairRunEntry{(PassKernel)k_contig_pair_run<12, 4, RMX_PAIR_RUN>, GEO::SMEM_BYTES, RMX_PAIR_RUN};
+        if (run >= 16) return prefetch ? pair_run_entry<16, true>() : pair_run_entry<16, false>();
+        return prefetch ? pair_run_entry<8, true>() : pair_run_entry<8, false>();
     }
     return PairRunEntry{nullptr, 0, 0};
 }

@@ -534,79 +534,6 @@ __global__ void __launch_bounds__(kThreads, (MODE == K_INV_ARGMAX_PRE && LOGE ==
 }
 
 // ---------------------------------------------------------------------------------------
-// innermost inverse pass, X_i-stationary: one CTA walks RUN consecutive pairs of one row
-// ---------------------------------------------------------------------------------------
-// Same arithmetic as k_contig<..., C_INV_PAIR> for one row per tile (n == TILE).  Pair lists are
-// ordered by first buoy (i < j, i-major), so consecutive pairs share X_i: the CTA keeps the X_i row
-// in registers and re-reads it only when i changes.  That removes ~8*(1 - 1/RUN) of the 24 bytes
-// per element this pass moves through L2 and L1 (it is bound by exactly that traffic), and the
-// per-row twiddle powers are computed once per CTA instead of once per pair.
-template <int LOGN, int LOGE, int RUN>
-__global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run(const PassParams p) {
-    using GEO = TileGeom<LOGN, LOGE, false>;
-    constexpr int E = GEO::E, NT = GEO::NT;
-    static_assert(GEO::G == 1 && GEO::NSTAGES >= 2, "one row per tile");
-    extern __shared__ float2 smem[];
-    __shared__ float2 s_pw[8];
-
-    const int i0 = threadIdx.x, g = 0;
-    const unsigned n_blocks = ((unsigned)p.n_items + RUN - 1) / RUN;
-    const unsigned blk = blockIdx.x % n_blocks;              // pair-block fastest: CTAs that run together share rows
-    const long long row = blockIdx.x / n_blocks;
-    const uint32_t rr = (uint32_t)row & ((1u << p.post_logn) - 1u);
-    if (p.post_logm > 0 && threadIdx.x < LOGE) {
-        const uint32_t mask = (p.post_logm >= 32) ? 0xffffffffu : ((1u << p.post_logm) - 1u);
-        s_pw[threadIdx.x] = unit_root((rr * ((uint32_t)NT << threadIdx.x)) & mask, p.post_logm, true);
-    }
-    float2 a[E];
-    int cur_i = -1;
-    const int first = (int)blk * RUN;
-    const int last = min(first + RUN, p.n_items);
-    for (int pidx = first; pidx < last; ++pidx) {
-        const int2 pr = __ldg(p.pairs + pidx);
-        if (pr.x != cur_i) {                                  // CTA-uniform
-            const float2* __restrict__ xi = p.spectra + ((long long)pr.x << p.logL) + (row << LOGN);
-#pragma unroll
-            for (int u = 0; u < E; ++u) a[u] = RMX_X_LOAD(xi + i0 + u * NT);
-            cur_i = pr.x;
-        }
-        const float2* __restrict__ xj = p.spectra + ((long long)pr.y << p.logL) + (row << LOGN);
-        float2 r[E];
-#pragma unroll
-        for (int u = 0; u < E; ++u) r[u] = cmul_conj(RMX_X_LOAD(xj + i0 + u * NT), a[u]);     // X_j * conj(X_i)
-        if (pidx != first) {
-            if (RMX_PAIR_RUN_BULK_STORE && threadIdx.x == 0) bulk_store_wait_read();   // previous row has left the buffer
-            __syncthreads();
-        }
-        fft_tile<GEO, true, (RMX_PAIR_TWTREE != 0)>(r, smem, g, i0, p.tabs);
-        if (p.post_logm > 0) {
-            float2 tw[E];
-            row_twiddles_shared<E>(tw, rr, (uint32_t)i0, p.post_logm, true, p.post_scale, s_pw);
-#pragma unroll
-            for (int u = 0; u < E; ++u) r[u] = cmul(r[u], tw[u]);
-        }
-        if (p.scale != 1.0f) {
-#pragma unroll
-            for (int u = 0; u < E; ++u) { r[u].x *= p.scale; r[u].y *= p.scale; }
-        }
-        float2* __restrict__ out = p.dst + (long long)pidx * p.src_item_stride + (row << LOGN);
-        if constexpr (RMX_PAIR_RUN_BULK_STORE) {
-            // row -> exchange buffer -> one bulk copy (TMA engine); it drains while the next pair loads
-            __syncthreads();                                 // every thread is past its last exchange read
-#pragma unroll
-            for (int u = 0; u < E; ++u) smem[i0 + u * NT] = r[u];
-            fence_proxy_async();
-            __syncthreads();
-            if (threadIdx.x == 0) bulk_store_1d(out, smem, (uint32_t)(GEO::N * sizeof(float2)));
-        } else {
-#pragma unroll
-            for (int u = 0; u < E; ++u) RMX_D_STORE(out + i0 + u * NT, r[u]);
-        }
-    }
-    if (RMX_PAIR_RUN_BULK_STORE && threadIdx.x == 0) bulk_store_wait_read();
-}
-
-// ---------------------------------------------------------------------------------------
 // TMA helpers (sm_100a): 2-D tiled bulk-tensor loads completing on an mbarrier
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
@@ -630,6 +557,116 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+// global -> shared bulk copy (TMA engine, 1-D): `bytes` a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_load_1d(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// innermost inverse pass, X_i-stationary: one CTA walks RUN consecutive pairs of one row
+// ---------------------------------------------------------------------------------------
+// Same arithmetic as k_contig<..., C_INV_PAIR> for one row per tile (n == TILE).  Pair lists are
+// ordered by first buoy (i < j, i-major), so consecutive pairs share X_i: the CTA keeps the X_i row
+// in registers and re-reads it only when i changes.  That removes ~8*(1 - 1/RUN) of the 24 bytes
+// per element this pass moves through L2 and L1 (it is bound by exactly that traffic), and the
+// per-row twiddle powers are computed once per CTA instead of once per pair.
+// PREFETCH: the X_j row of the NEXT pair of the run is brought into a 32 KB landing buffer by one bulk copy
+// (TMA engine, completes on an mbarrier) while the CTA transforms the current pair, so only the first pair of a
+// run waits for its spectrum row and no registers are tied up by loads in flight.
+template <int LOGN, int LOGE, int RUN, bool PREFETCH>
+__global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run(const PassParams p) {
+    using GEO = TileGeom<LOGN, LOGE, false>;
+    constexpr int E = GEO::E, NT = GEO::NT;
+    static_assert(GEO::G == 1 && GEO::NSTAGES >= 2, "one row per tile");
+    extern __shared__ float2 smem[];
+    __shared__ float2 s_pw[8];
+    __shared__ __align__(8) unsigned long long mbar;
+    constexpr uint32_t ROW_BYTES = (uint32_t)(GEO::N * sizeof(float2));
+    // landing buffer behind the exchange area, 128-byte aligned
+    float2* land = smem + ((GEO::NP + 15) & ~15);
+
+    const int i0 = threadIdx.x, g = 0;
+    const unsigned n_blocks = ((unsigned)p.n_items + RUN - 1) / RUN;
+    const unsigned blk = blockIdx.x % n_blocks;              // pair-block fastest: CTAs that run together share rows
+    const long long row = blockIdx.x / n_blocks;
+    const uint32_t rr = (uint32_t)row & ((1u << p.post_logn) - 1u);
+    if (p.post_logm > 0 && threadIdx.x < LOGE) {
+        const uint32_t mask = (p.post_logm >= 32) ? 0xffffffffu : ((1u << p.post_logm) - 1u);
+        s_pw[threadIdx.x] = unit_root((rr * ((uint32_t)NT << threadIdx.x)) & mask, p.post_logm, true);
+    }
+    float2 a[E];
+    int cur_i = -1;
+    const int first = (int)blk * RUN;
+    const int last = min(first + RUN, p.n_items);
+    uint32_t parity = 0;
+    if constexpr (PREFETCH) {
+        if (threadIdx.x == 0) {
+            mbar_init(&mbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const int2 pr0 = __ldg(p.pairs + first);
+            mbar_expect_tx(&mbar, ROW_BYTES);
+            bulk_load_1d(land, p.spectra + ((long long)pr0.y << p.logL) + (row << LOGN), ROW_BYTES, &mbar);
+        }
+        __syncthreads();                                      // the barrier is initialised before anyone waits on it
+    }
+    for (int pidx = first; pidx < last; ++pidx) {
+        const int2 pr = __ldg(p.pairs + pidx);
+        if (pr.x != cur_i) {                                  // CTA-uniform
+            const float2* __restrict__ xi = p.spectra + ((long long)pr.x << p.logL) + (row << LOGN);
+#pragma unroll
+            for (int u = 0; u < E; ++u) a[u] = RMX_X_LOAD(xi + i0 + u * NT);
+            cur_i = pr.x;
+        }
+        float2 r[E];
+        if constexpr (PREFETCH) {
+            mbar_wait(&mbar, parity);
+            parity ^= 1u;
+#pragma unroll
+            for (int u = 0; u < E; ++u) r[u] = cmul_conj(land[i0 + u * NT], a[u]);            // X_j * conj(X_i)
+            __syncthreads();          // landing buffer consumed; also: everyone is past the previous pair's last exchange read
+            if (threadIdx.x == 0 && pidx + 1 < last) {
+                const int2 prn = __ldg(p.pairs + pidx + 1);
+                fence_proxy_async();
+                mbar_expect_tx(&mbar, ROW_BYTES);
+                bulk_load_1d(land, p.spectra + ((long long)prn.y << p.logL) + (row << LOGN), ROW_BYTES, &mbar);
+            }
+        } else {
+            const float2* __restrict__ xj = p.spectra + ((long long)pr.y << p.logL) + (row << LOGN);
+#pragma unroll
+            for (int u = 0; u < E; ++u) r[u] = cmul_conj(RMX_X_LOAD(xj + i0 + u * NT), a[u]);     // X_j * conj(X_i)
+            if (pidx != first) {
+                if (RMX_PAIR_RUN_BULK_STORE && threadIdx.x == 0) bulk_store_wait_read();   // previous row has left the buffer
+                __syncthreads();
+            }
+        }
+        fft_tile<GEO, true, (RMX_PAIR_TWTREE != 0)>(r, smem, g, i0, p.tabs);
+        if (p.post_logm > 0) {
+            float2 tw[E];
+            row_twiddles_shared<E>(tw, rr, (uint32_t)i0, p.post_logm, true, p.post_scale, s_pw);
+#pragma unroll
+            for (int u = 0; u < E; ++u) r[u] = cmul(r[u], tw[u]);
+        }
+        if (p.scale != 1.0f) {
+#pragma unroll
+            for (int u = 0; u < E; ++u) { r[u].x *= p.scale; r[u].y *= p.scale; }
+        }
+        float2* __restrict__ out = p.dst + (long long)pidx * p.src_item_stride + (row << LOGN);
+        if constexpr (RMX_PAIR_RUN_BULK_STORE && !PREFETCH) {
+            // row -> exchange buffer -> one bulk copy (TMA engine); it drains while the next pair loads
+            __syncthreads();                                 // every thread is past its last exchange read
+#pragma unroll
+            for (int u = 0; u < E; ++u) smem[i0 + u * NT] = r[u];
+            fence_proxy_async();
+            __syncthreads();
+            if (threadIdx.x == 0) bulk_store_1d(out, smem, (uint32_t)(GEO::N * sizeof(float2)));
+        } else {
+#pragma unroll
+            for (int u = 0; u < E; ++u) RMX_D_STORE(out + i0 + u * NT, r[u]);
+        }
+    }
+    if (RMX_PAIR_RUN_BULK_STORE && !PREFETCH && threadIdx.x == 0) bulk_store_wait_read();
 }
 
 // ---------------------------------------------------------------------------------------

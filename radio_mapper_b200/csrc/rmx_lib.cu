@@ -74,6 +74,12 @@ struct rmx_plan {
     bool force_full_search = false;   // true: never take the one-pass windowed path
     StageTables welch_row_tabs;       // 8192-point row transform of the cluster Welch kernel (built on first use)
     bool welch_row_tabs_ready = false;
+    unsigned flags = 0;               // RMX_PLAN_* given to rmx_plan_create
+    // tuning knobs (rmx_plan_set_option)
+    int pair_run = 8;                 // pairs walked by one CTA of the X_i-stationary row pass (8 or 16)
+    int pair_prefetch = 1;            // next X_j row by bulk copy into shared memory
+    long long fwd_group_bytes = 0;    // forward passes run over groups of signals whose spectra fit this many bytes (0 = all at once)
+    int welch_clusters = 0;           // resident clusters of the Welch kernel (0 = occupancy query)
 };
 
 static int build_stage_tables(rmx_plan* pl, int logn, int loge, StageTables* out) {
@@ -126,7 +132,7 @@ static int choose_passes(rmx_plan* pl) {
     // one (B200, L = 2^22), and the column pass of length 512/1024 takes the TMA-fed kernel.
     if (logL - 12 >= 5 && logL - 12 <= maxk) maxc = 12;
     if (logL - 13 > maxk) maxc = 12;        // three passes: the 4096-point row kernels are ~15 % faster per element (cfg5)
-    { const char* e = getenv("RMX_CONTIG_LOGN"); if (e && atoi(e) >= 8 && atoi(e) <= max_contig_logn(5)) maxc = atoi(e); }   // developer override
+    { const int e = (int)((pl->flags >> 8) & 0x1fu); if (e >= 8 && e <= max_contig_logn(5)) maxc = e; }   // RMX_PLAN_ROW_LOGN: developer override
     if (logL < minn) return fail(RMX_ERR_UNSUPPORTED, "fft_len 2^%d is below the minimum 2^%d", logL, minn);
     if (logL <= maxc) {
         pl->n_passes = 1;
@@ -166,8 +172,8 @@ extern "C" int rmx_plan_create(rmx_plan** out, int n_signals, size_t n_samples, 
     if (n_samples == 0 || n_samples > fft_len) return fail(RMX_ERR_ARG, "need 0 < n_samples <= fft_len");
     if (fft_len & (fft_len - 1)) return fail(RMX_ERR_UNSUPPORTED, "fft_len must be a power of two (got %zu)", fft_len);
     if (fft_len > (size_t(1) << 30)) return fail(RMX_ERR_UNSUPPORTED, "fft_len above 2^30 is not supported");
-    (void)flags;
     rmx_plan* pl = new rmx_plan();
+    pl->flags = flags;
     pl->n_signals = n_signals;
     pl->n_samples = (long long)n_samples;
     pl->logL = 0;
@@ -185,6 +191,8 @@ extern "C" int rmx_plan_create(rmx_plan** out, int n_signals, size_t n_samples, 
 
 extern "C" int rmx_plan_destroy(rmx_plan* pl) {
     if (!pl) return RMX_OK;
+    // launches that still read the plan's twiddle tables / window may be queued on any stream
+    if (!pl->dev_allocs.empty()) cudaDeviceSynchronize();
     for (void* p : pl->dev_allocs) cudaFree(p);
     for (auto& r : pl->prof_records) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
     for (auto e : pl->prof_pool) cudaEventDestroy(e);
@@ -258,6 +266,16 @@ extern "C" size_t rmx_plan_workspace_bytes(const rmx_plan* pl, int n_pairs) {
     if (w.mode >= 0) return (size_t)n_pairs * (w.n_chunks + 1) * w.slots * sizeof(float2) + 256;
     const size_t L = size_t(1) << pl->logL;
     return (size_t)n_pairs * (L * sizeof(float2) + (size_t)tiles_per_item_pass0(pl) * sizeof(Partial)) + 256;
+}
+
+extern "C" int rmx_plan_set_option(rmx_plan* pl, const char* name, long long value) {
+    if (!pl || !name) return fail(RMX_ERR_ARG, "null argument to rmx_plan_set_option");
+    if (!strcmp(name, "pair_run")) { if (value != 8 && value != 16) return fail(RMX_ERR_ARG, "pair_run must be 8 or 16"); pl->pair_run = (int)value; }
+    else if (!strcmp(name, "pair_prefetch")) pl->pair_prefetch = value != 0;
+    else if (!strcmp(name, "fwd_group_bytes")) pl->fwd_group_bytes = value < 0 ? 0 : value;
+    else if (!strcmp(name, "welch_clusters")) pl->welch_clusters = (int)std::max<long long>(0, value);
+    else return fail(RMX_ERR_ARG, "unknown plan option '%s'", name);
+    return RMX_OK;
 }
 
 extern "C" int rmx_plan_set_search_mode(rmx_plan* pl, int force_full) {
@@ -350,19 +368,19 @@ static PassParams base_params(const rmx_plan* pl) {
     return pp;
 }
 
-// Developer switches (read per call so one process can A/B the kernel variants; see
-// tests/test_gpu_parity.py::test_kernel_variants_agree):
-//   RMX_TWIDDLE_IN_COL  inter-pass twiddles on the input of the column pass instead of the row pass output
-//   RMX_NO_TMA          arg-max pass through per-thread strided loads instead of the TMA-fed kernel
-//   RMX_NO_PAIR_RUN     one pair per CTA in the 4096-point row pass instead of the X_i-stationary walk
-//   RMX_CONTIG_LOGN     (plan creation) force the row length of multi-pass plans
-static bool twiddle_in_contig() { return getenv("RMX_TWIDDLE_IN_COL") == nullptr; }
+// Developer switches are plan flags (rmx_plan_create, include/rmx.h), fixed for the life of a plan: one process
+// can A/B the kernel variants by creating two plans (tests/test_gpu_parity.py::test_kernel_variants_agree):
+//   RMX_PLAN_TWIDDLE_IN_COL  inter-pass twiddles on the input of the column pass instead of the row pass output
+//   RMX_PLAN_NO_TMA          arg-max pass through per-thread strided loads instead of the TMA-fed kernel
+//   RMX_PLAN_NO_PAIR_RUN     one pair per CTA in the 4096-point row pass instead of the X_i-stationary walk
+//   RMX_PLAN_ROW_LOGN(n)     force the row length of multi-pass plans
+static bool twiddle_in_contig(const rmx_plan* pl) { return (pl->flags & RMX_PLAN_TWIDDLE_IN_COL) == 0; }
 
 // The contiguous inverse pass (C_INV_PAIR) also applies the input twiddles -- and, for two-pass plans,
 // the 1/L -- of the column pass that runs next (pass n_passes-2); that pass is launched pre_twiddled.
 static void set_post_twiddle(const rmx_plan* pl, PassParams* pp) {
     const int np = pl->n_passes;
-    if (np < 2 || !twiddle_in_contig()) return;
+    if (np < 2 || !twiddle_in_contig(pl)) return;
     const int t = np - 2;
     pp->post_logm = pl->logn[t] + pl->logs[t];
     pp->post_logn = pl->logn[t];
@@ -404,7 +422,7 @@ static int sm_count() {
 // (without setting an error) when this plan / pointer cannot take that path
 static int launch_argmax_tma(const rmx_plan* pl, const PassParams& pp, bool pre, int cnt, cudaStream_t st, bool* taken) {
     *taken = false;
-    if (getenv("RMX_NO_TMA")) return RMX_OK;
+    if (pl->flags & RMX_PLAN_NO_TMA) return RMX_OK;
     const TmaKernelEntry k = get_argmax_tma_kernel(pl->logn[0], pl->loge[0], pre);
     auto enc = tensor_map_encoder();
     if (!k.fn || !enc) return RMX_OK;
@@ -436,8 +454,10 @@ static int launch_argmax_tma(const rmx_plan* pl, const PassParams& pp, bool pre,
 // innermost inverse pass over `cnt` pairs
 static int launch_pair_pass(const rmx_plan* pl, const PassParams& pp, int cnt, cudaStream_t st) {
     const int last = pl->n_passes - 1;
-    const PairRunEntry kr = get_pair_run_kernel(pl->logn[last], pl->loge[last]);
-    if (kr.fn && pl->n_passes >= 2 && !getenv("RMX_NO_PAIR_RUN")) {
+    // the bulk-copy prefetch needs 16-byte aligned spectrum rows (rows are multiples of 32 KB apart)
+    const bool prefetch = pl->pair_prefetch != 0 && (reinterpret_cast<uintptr_t>(pp.spectra) & 15) == 0;
+    const PairRunEntry kr = get_pair_run_kernel(pl->logn[last], pl->loge[last], pl->pair_run, prefetch);
+    if (kr.fn && pl->n_passes >= 2 && !(pl->flags & RMX_PLAN_NO_PAIR_RUN)) {
         const long long rows = 1LL << (pl->logL - pl->logn[last]);
         const long long blocks = (cnt + kr.run - 1) / kr.run;
         return launch_pass(pl, KernelEntry{kr.fn, kr.smem_bytes, 0}, "contig_inv_pair", dim3((unsigned)(rows * blocks)), pp, st);
@@ -463,16 +483,32 @@ static int forward_cu8(const rmx_plan* pl, const uint8_t* iq, long long stride_b
         return launch_pass(pl, get_contig_kernel(pl->logn[0], pl->loge[0], C_FWD_CU8), "contig_fwd_cu8",
                            dim3(tiles_of(pl, 0, n_items)), pp, st);
     }
-    for (int t = 0; t < np - 1; ++t) {
-        pp.tabs = pl->tabs[t];
-        pp.logS = pl->logs[t];
-        int rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], t == 0 ? K_FWD_CU8 : K_FWD),
-                             t == 0 ? "col_fwd_cu8" : "col_fwd", dim3(tiles_of(pl, t, n_items)), pp, st);
+    // Groups of signals whose spectra fit `fwd_group_bytes` run their passes back to back, so the output of one
+    // pass is still in L2 when the next pass reads it (the passes are in place: the spectrum is written to HBM once).
+    const long long L = 1LL << pl->logL;
+    int group = n_items;
+    if (pl->fwd_group_bytes > 0)
+        group = (int)std::max<long long>(1, std::min<long long>(n_items, pl->fwd_group_bytes / (L * (long long)sizeof(float2))));
+    const long long stride = pp.cu8_stride;
+    for (int first = 0; first < n_items; first += group) {
+        const int cnt = std::min(group, n_items - first);
+        pp.n_items = cnt;
+        pp.cu8 = iq + (long long)first * stride;
+        pp.dst = spectra + (long long)first * L;
+        pp.src = pp.dst;
+        for (int t = 0; t < np - 1; ++t) {
+            pp.tabs = pl->tabs[t];
+            pp.logS = pl->logs[t];
+            int rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], t == 0 ? K_FWD_CU8 : K_FWD),
+                                 t == 0 ? "col_fwd_cu8" : "col_fwd", dim3(tiles_of(pl, t, cnt)), pp, st);
+            if (rc) return rc;
+        }
+        pp.tabs = pl->tabs[np - 1];
+        int rc = launch_pass(pl, get_contig_kernel(pl->logn[np - 1], pl->loge[np - 1], C_FWD), "contig_fwd",
+                             dim3(tiles_of(pl, np - 1, cnt)), pp, st);
         if (rc) return rc;
     }
-    pp.tabs = pl->tabs[np - 1];
-    return launch_pass(pl, get_contig_kernel(pl->logn[np - 1], pl->loge[np - 1], C_FWD), "contig_fwd",
-                       dim3(tiles_of(pl, np - 1, n_items)), pp, st);
+    return RMX_OK;
 }
 
 extern "C" int rmx_fft_forward_cu8(const rmx_plan* pl, const uint8_t* iq, size_t signal_stride_bytes,
@@ -776,7 +812,7 @@ extern "C" int rmx_xcorr_pairs_peak(const rmx_plan* pl, const rmx_complex64* spe
             pp.tabs = pl->tabs[t];
             pp.logS = pl->logs[t];
             pp.scale = t == 0 ? inv_len : 1.0f;
-            const bool pre = (t == np - 2) && twiddle_in_contig();      // twiddled by the contiguous pass
+            const bool pre = (t == np - 2) && twiddle_in_contig(pl);      // twiddled by the contiguous pass
             if (t == 0) {
                 bool taken = false;
                 rc = launch_argmax_tma(pl, pp, pre, cnt, st, &taken);
@@ -799,8 +835,8 @@ extern "C" int rmx_xcorr_pairs_peak(const rmx_plan* pl, const rmx_complex64* spe
                 // two-pass plans: the workspace (input of pass 0) is pre-twiddled and already scaled
                 k_finalize_sum<<<cnt, 128, 0, st>>>(partials, tpi, D, pl->logL, pl->logn[0], pl->logs[0],
                                                     (int)pl->lag_pos_max, (int)pl->lag_neg_max,
-                                                    (np == 2 && twiddle_in_contig()) ? 1.0f : inv_len,
-                                                    (np == 2 && twiddle_in_contig()) ? 1 : 0, out + first);
+                                                    (np == 2 && twiddle_in_contig(pl)) ? 1.0f : inv_len,
+                                                    (np == 2 && twiddle_in_contig(pl)) ? 1 : 0, out + first);
             }
             LAUNCH_CHECK("finalize_sum");
         }
@@ -830,7 +866,7 @@ extern "C" int rmx_xcorr_full(const rmx_plan* pl, const rmx_complex64* spectra, 
         pp.tabs = pl->tabs[t];
         pp.logS = pl->logs[t];
         pp.scale = t == 0 ? inv_len : 1.0f;
-        rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], (t == np - 2 && twiddle_in_contig()) ? K_INV_PRE : K_INV), "col_inv", dim3(tiles_of(pl, t, n_pairs)), pp, st);
+        rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], (t == np - 2 && twiddle_in_contig(pl)) ? K_INV_PRE : K_INV), "col_inv", dim3(tiles_of(pl, t, n_pairs)), pp, st);
     }
     return rc;
 }
@@ -1069,6 +1105,12 @@ extern "C" size_t rmx_welch_workspace_bytes(const rmx_plan* pl, int segments_in_
     return L * sizeof(float) + (size_t)segments_in_flight * L * sizeof(float2) + 512;
 }
 
+extern "C" int rmx_welch_path(const rmx_plan* pl, const uint8_t* iq) {
+    if (!pl) return fail(RMX_ERR_ARG, "plan is null");
+    const WelchClusterEntry k = get_welch_cluster_kernel(pl->logL - 13);
+    return (k.fn && !(pl->flags & RMX_PLAN_NO_WELCH_CLUSTER) && (reinterpret_cast<uintptr_t>(iq) & 7) == 0) ? 1 : 0;
+}
+
 extern "C" int rmx_welch_psd(rmx_plan* pl, const uint8_t* iq, float* psd, double sample_rate, void* workspace,
                              size_t workspace_bytes, void* stream) {
     if (!pl || !iq || !psd || !workspace) return fail(RMX_ERR_ARG, "null argument to rmx_welch_psd");
@@ -1086,7 +1128,7 @@ extern "C" int rmx_welch_psd(rmx_plan* pl, const uint8_t* iq, float* psd, double
     {
         // one-kernel path: nperseg = C * 8192 with a cluster of C = 2, 4 or 8 CTAs holding the segment on chip
         const WelchClusterEntry k = get_welch_cluster_kernel(pl->logL - 13);
-        if (k.fn && !getenv("RMX_NO_WELCH_CLUSTER") && (reinterpret_cast<uintptr_t>(iq) & 7) == 0) {
+        if (k.fn && rmx_welch_path(pl, iq) == 1) {
             if (!pl->welch_row_tabs_ready) {
                 rc = build_stage_tables(pl, 13, 5, &pl->welch_row_tabs);
                 if (rc) return rc;
@@ -1121,7 +1163,7 @@ extern "C" int rmx_welch_psd(rmx_plan* pl, const uint8_t* iq, float* psd, double
                 cudaGetLastError();
                 max_clusters = std::max(1, sm_count() / k.cluster);
             }
-            { const char* e = getenv("RMX_WELCH_CLUSTERS"); if (e && atoi(e) > 0) max_clusters = atoi(e); }
+            if (pl->welch_clusters > 0) max_clusters = pl->welch_clusters;
             const int n_clusters = std::min(pl->n_signals, max_clusters);
             cfg.gridDim = dim3((unsigned)(n_clusters * k.cluster));
             {

@@ -98,13 +98,15 @@ class BuoySignalDetector:
         self._plans = {}
 
     def detect_block(self, iq_u8, center_freq_mhz: float, iso_timestamp: Optional[str] = None,
-                     gps_ns: Optional[int] = None) -> List[SignalDetection]:
+                     gps_ns: Optional[int] = None, timestamps=None) -> List[SignalDetection]:
         """Detections of one raw cu8 block, in increasing bin order (like the reference loop)."""
-        return self.detect_block_indexed(iq_u8, center_freq_mhz, iso_timestamp, gps_ns)[1]
+        return self.detect_block_indexed(iq_u8, center_freq_mhz, iso_timestamp, gps_ns, timestamps)[1]
 
     def detect_block_indexed(self, iq_u8, center_freq_mhz: float, iso_timestamp: Optional[str] = None,
-                             gps_ns: Optional[int] = None):
-        """-> (FFT bin of each detection, detections)."""
+                             gps_ns: Optional[int] = None, timestamps=None):
+        """-> (FFT bin of each detection, detections).  `timestamps`: optional callable returning
+        (iso_timestamp, gps_ns), called once per detection like the reference's
+        gps_source.get_precise_timestamp() (buoy_node.py:436)."""
         center_freq_hz = int(center_freq_mhz * 1e6)                       # :365
         db_dev, n = _spectrum_from_cu8(iq_u8, self._plans)
         spec = _BlockSpectrum(db_dev, self.detection_threshold_dbm, 10)   # :411-415
@@ -125,6 +127,8 @@ class BuoySignalDetector:
                 continue
             f_mhz = f_hz / 1e6
             bins.append(int(k))
+            if timestamps is not None:
+                iso_timestamp, gps_ns = timestamps()
             out.append(SignalDetection(buoy_id=self.buoy_id, frequency_mhz=round(f_mhz, 3),
                                        signal_strength_dbm=round(power, 1), timestamp_utc=iso_timestamp,
                                        gps_timestamp_ns=gps_ns, lat=self.lat, lng=self.lng,
@@ -230,8 +234,9 @@ class StreamSignalDetector:
         self.lat, self.lng = 35.4676, -97.5164          # :173-174
         self._plans = {}
 
-    def _estimate_bandwidth(self, p_db: np.ndarray, peak_idx: int) -> float:
+    def _estimate_bandwidth(self, power_spectrum_db: np.ndarray, peak_idx: int) -> float:
         """-3 dB walk left and right of the peak (:254-278)."""
+        p_db = power_spectrum_db
         thr = p_db[peak_idx] - 3.0
         left = right = int(peak_idx)
         last = len(p_db) - 1

@@ -70,7 +70,10 @@ class Plan:
     """Batched FFT / correlation plan for `n_signals` signals of `n_samples` samples each,
     zero-padded to `fft_len` (power of two)."""
 
-    def __init__(self, n_signals: int, n_samples: int, fft_len: Optional[int] = None, device=None):
+    def __init__(self, n_signals: int, n_samples: int, fft_len: Optional[int] = None, device=None,
+                 flags: Optional[int] = None, options: Optional[dict] = None):
+        """flags: RMX_PLAN_* developer switches (default: taken once from the RMX_* environment variables, see
+        _native.flags_from_env); options: {name: value} for rmx_plan_set_option."""
         if not torch.cuda.is_available():
             raise RuntimeError("radio_mapper_b200 needs a CUDA device (no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -78,9 +81,12 @@ class Plan:
         self.n_samples = int(n_samples)
         self.fft_len = int(fft_len) if fft_len is not None else correlation_fft_len(n_samples)
         self._h = ctypes.c_void_p()
+        self.flags = _native.flags_from_env() if flags is None else int(flags)
         with torch.cuda.device(self.device):
-            _native.check(_lib.rmx_plan_create(ctypes.byref(self._h), self.n_signals, self.n_samples, self.fft_len, 0),
+            _native.check(_lib.rmx_plan_create(ctypes.byref(self._h), self.n_signals, self.n_samples, self.fft_len, self.flags),
                           "rmx_plan_create")
+        for name, value in (options or {}).items():
+            self.set_option(name, value)
         buf = (ctypes.c_int32 * 8)()
         n = _native.check(_lib.rmx_plan_layout(self._h, buf, 8), "rmx_plan_layout")
         self.pass_lengths = [int(buf[i]) for i in range(n)]
@@ -88,12 +94,19 @@ class Plan:
         self.max_lag: Optional[int] = None
 
     def __del__(self):
+        # rmx_plan_destroy synchronises the device before freeing the plan's tables (launches that read them
+        # may still be queued)
         h, self._h = getattr(self, "_h", None), None
         if h:
             try:
-                _lib.rmx_plan_destroy(h)
+                with torch.cuda.device(self.device):
+                    _lib.rmx_plan_destroy(h)
             except Exception:
                 pass
+
+    def set_option(self, name: str, value: int):
+        """Tuning knob of the plan (include/rmx.h: rmx_plan_set_option)."""
+        _native.check(_lib.rmx_plan_set_option(self._h, name.encode(), int(value)), "rmx_plan_set_option(%s)" % name)
 
     # ---- layout ------------------------------------------------------------------------
     def layout_freq_index(self) -> np.ndarray:
@@ -228,12 +241,13 @@ class Plan:
         segments_in_flight bounds the spectra workspace (8*fft_len bytes per segment); the default takes as many
         segments per launch as fit 1 GiB -- fewer, larger launches measured faster on B200 (1000 x 64k bins:
         0.36 ms with all segments in flight, 0.45 ms with 256, 0.69 ms with 64)."""
+        _require_cuda(iq_u8, torch.uint8, "iq_u8")
         if segments_in_flight is None:
             # nperseg = 2/4/8 * 8192 runs as one thread-block-cluster kernel that keeps each segment in
-            # distributed shared memory and needs no spectra workspace at all
-            single_kernel = self.fft_len in (1 << 14, 1 << 15, 1 << 16) and not os.environ.get("RMX_NO_WELCH_CLUSTER")
+            # distributed shared memory and needs no spectra workspace at all; the library says which path this
+            # plan and input pointer take (an unaligned view falls back to two passes and then needs the workspace)
+            single_kernel = _lib.rmx_welch_path(self._h, _ptr(iq_u8)) == 1
             segments_in_flight = 1 if single_kernel else max(1, (1 << 30) // (8 * self.fft_len))
-        _require_cuda(iq_u8, torch.uint8, "iq_u8")
         if self.n_samples != self.fft_len:
             raise ValueError("Welch plans need n_samples == fft_len")
         if iq_u8.numel() != self.n_signals * 2 * self.fft_len:

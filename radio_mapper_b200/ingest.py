@@ -165,6 +165,7 @@ class StreamingCorrelator:
         self._en_host = torch.empty((self.depth + 1, B), dtype=torch.int64).pin_memory()
         self.windows_done = 0
         self.h2d_bytes = 0
+        self._dirty = False             # True while a run() is in progress or was abandoned with windows in flight
 
     def run(self, source, max_lag: Optional[int] = None, max_windows: Optional[int] = None) -> Iterator[np.ndarray]:
         cor = self.cor
@@ -181,6 +182,13 @@ class StreamingCorrelator:
         pending: List = []              # (result slot, done_event) in window order
         with torch.cuda.device(self.device):
             compute = torch.cuda.current_stream()
+            # A consumer that stopped iterating an earlier run() early left windows in flight: their kernels and
+            # result copies may still be using the device / pinned slots this run is about to overwrite.
+            self._copy_stream.wait_stream(compute)
+            if self._dirty:
+                compute.synchronize()
+                self._copy_stream.synchronize()
+            self._dirty = True
             w = 0
             while max_windows is None or w < max_windows:
                 s = w % D
@@ -218,6 +226,7 @@ class StreamingCorrelator:
                     yield self._finish(pending.pop(0))
             while pending:
                 yield self._finish(pending.pop(0))
+            self._dirty = False                                # ran to completion: nothing left in flight
 
     def _finish(self, item) -> np.ndarray:
         r, done = item

@@ -42,32 +42,42 @@ def shard_units(n_windows: int, n_pairs: int, world: int, rank: int) -> Tuple[Li
     return list(range(n_windows)), slice(a, b)
 
 
-def gather_records(rec: torch.Tensor, energy: torch.Tensor, n_windows: int, n_pairs: int, world: int, rank: int):
-    """Assemble the full [W, P, 4] record tensor (and [W, B] energies) on every rank.
+def _all_gather_flat(flat: torch.Tensor, world: int) -> torch.Tensor:
+    """ONE collective: every rank contributes `flat` (1-D, same length everywhere); returns [world, len]."""
+    buf = flat.new_empty((world, flat.numel()))
+    try:
+        dist.all_gather_into_tensor(buf, flat)
+    except (RuntimeError, AttributeError, NotImplementedError):          # backend without the tensor form
+        dist.all_gather(list(buf.unbind(0)), flat)
+    return buf
 
-    rec: this rank's [w_local, p_local, 4] int32; energy: [w_local, B] int64."""
+
+def gather_records(rec: torch.Tensor, energy: torch.Tensor, n_windows: int, n_pairs: int, world: int, rank: int):
+    """Assemble the full [W, P, 4] record tensor (and [W, B] energies) on every rank with ONE all-gather.
+
+    rec: this rank's [w_local, p_local, 4] int32; energy: [w_local, B] int64.  Records and energies travel in one
+    padded int32 buffer (an int64 energy is two int32 words), so a step costs a single latency-bound collective."""
     by_window = n_windows >= world
     if by_window:
         sizes = [split_even(n_windows, world, r) for r in range(world)]
         width = max(b - a for a, b in sizes)
-        pad_rec = rec.new_zeros((width,) + tuple(rec.shape[1:]))
-        pad_rec[: rec.shape[0]] = rec
-        pad_en = energy.new_zeros((width,) + tuple(energy.shape[1:]))
-        pad_en[: energy.shape[0]] = energy
-        recs = [torch.empty_like(pad_rec) for _ in range(world)]
-        ens = [torch.empty_like(pad_en) for _ in range(world)]
-        dist.all_gather(recs, pad_rec)
-        dist.all_gather(ens, pad_en)
-        full_rec = torch.cat([recs[r][: b - a] for r, (a, b) in enumerate(sizes)], dim=0)
-        full_en = torch.cat([ens[r][: b - a] for r, (a, b) in enumerate(sizes)], dim=0)
+        n_rec = width * rec.shape[1] * rec.shape[2]
+        n_en = width * energy.shape[1] * 2
+        flat = rec.new_zeros(n_rec + n_en)
+        flat[: rec.numel()] = rec.reshape(-1)
+        flat[n_rec: n_rec + 2 * energy.numel()] = energy.contiguous().view(torch.int32).reshape(-1)
+        buf = _all_gather_flat(flat, world)
+        recs = buf[:, :n_rec].reshape(world, width, rec.shape[1], rec.shape[2])
+        ens = buf[:, n_rec:].contiguous().view(torch.int64).reshape(world, width, energy.shape[1])
+        full_rec = torch.cat([recs[r, : b - a] for r, (a, b) in enumerate(sizes)], dim=0)
+        full_en = torch.cat([ens[r, : b - a] for r, (a, b) in enumerate(sizes)], dim=0)
         return full_rec, full_en
     sizes = [split_even(n_pairs, world, r) for r in range(world)]
     width = max(b - a for a, b in sizes)
     pad_rec = rec.new_zeros((rec.shape[0], width, rec.shape[2]))
     pad_rec[:, : rec.shape[1]] = rec
-    recs = [torch.empty_like(pad_rec) for _ in range(world)]
-    dist.all_gather(recs, pad_rec)
-    full_rec = torch.cat([recs[r][:, : b - a] for r, (a, b) in enumerate(sizes)], dim=1)
+    buf = _all_gather_flat(pad_rec.reshape(-1), world).reshape(world, rec.shape[0], width, rec.shape[2])
+    full_rec = torch.cat([buf[r, :, : b - a] for r, (a, b) in enumerate(sizes)], dim=1)
     return full_rec, energy          # every rank computed all energies of its windows
 
 
@@ -142,7 +152,34 @@ def tile_pairs(n_buoys: int, world: int):
     return out
 
 
+_tile_cache: dict = {}
 _gather_perm_cache: dict = {}
+
+
+def tiles_for(n_buoys: int, world: int):
+    """tile_pairs(n_buoys, world), computed once per (n_buoys, world): the table depends on nothing else."""
+    key = (int(n_buoys), int(world))
+    tiles = _tile_cache.get(key)
+    if tiles is None:
+        if len(_tile_cache) >= 16:
+            _tile_cache.clear()
+        tiles = _tile_cache[key] = tile_pairs(*key)
+        for r, t in enumerate(tiles):
+            t["key"] = key + (r,)              # content key: (n_buoys, world, rank) identifies the tile
+    return tiles
+
+
+def _tiles_key(tiles, n_pairs: int, world: int):
+    """Content key of a tiling (never id(): ids are reused after garbage collection)."""
+    keys = tuple(t.get("key") for t in tiles)
+    if all(k is not None for k in keys):
+        return keys
+    import hashlib
+    h = hashlib.sha1()
+    for t in tiles:
+        h.update(np.ascontiguousarray(t["global_index"]).tobytes())
+        h.update(b"|")
+    return (n_pairs, world, h.hexdigest())
 
 
 def gather_tiled_records(rec: torch.Tensor, tiles, n_pairs: int, world: int):
@@ -150,17 +187,17 @@ def gather_tiled_records(rec: torch.Tensor, tiles, n_pairs: int, world: int):
     order on every rank: one padded all_gather into a single buffer, then one index_select with a cached
     permutation (the index lists are known to every rank)."""
     width = max(len(t["global_index"]) for t in tiles)
-    key = (id(tiles), str(rec.device), width)
+    key = (_tiles_key(tiles, n_pairs, world), str(rec.device), width)
     perm = _gather_perm_cache.get(key)
     if perm is None:
         src = np.empty(n_pairs, dtype=np.int64)                 # position of pair g in the concatenated padded buffers
         for r, t in enumerate(tiles):
             src[t["global_index"]] = r * width + np.arange(len(t["global_index"]))
+        if len(_gather_perm_cache) >= 32:
+            _gather_perm_cache.clear()
         perm = _gather_perm_cache[key] = torch.from_numpy(src).to(rec.device)
     pad = rec.new_zeros((rec.shape[0], width, rec.shape[2]))
     pad[:, : rec.shape[1]] = rec
-    buf = rec.new_empty((world, rec.shape[0], width, rec.shape[2]))
-    dist.all_gather_into_tensor(buf, pad) if hasattr(dist, "all_gather_into_tensor") and rec.is_cuda else \
-        dist.all_gather(list(buf.unbind(0)), pad)
+    buf = _all_gather_flat(pad.reshape(-1), world).reshape(world, rec.shape[0], width, rec.shape[2])
     cat = buf.permute(1, 0, 2, 3).reshape(rec.shape[0], world * width, rec.shape[2])
     return cat.index_select(1, perm)

@@ -26,6 +26,13 @@ def _torch():
     return torch
 
 
+def plt_backend_is_set() -> bool:
+    """True when the caller (or the environment) has already chosen a matplotlib backend."""
+    import os
+    import sys
+    return "matplotlib.pyplot" in sys.modules or bool(os.environ.get("MPLBACKEND"))
+
+
 class SignalAnalyzer:
     """Spectrum analysis of RTL-SDR cu8 captures on the GPU."""
 
@@ -52,6 +59,11 @@ class SignalAnalyzer:
         try:
             raw = np.fromfile(filename, dtype=np.uint8)
             torch = _torch()
+            if raw.size % 2:
+                # the reference's i_samples + 1j*q_samples raises on the I/Q length mismatch of an odd byte
+                # count and lands in its except branch (:43-45): same contract here
+                raise ValueError("operands could not be broadcast together with shapes (%d,) (%d,)"
+                                 % ((raw.size + 1) // 2, raw.size // 2))
             n = raw.size // 2
             dev = _engine().unpack_cu8(torch.from_numpy(raw[: 2 * n]).to(self._device()))
             samples = dev.cpu().numpy()
@@ -105,7 +117,8 @@ class SignalAnalyzer:
     def plot_spectrum(self, frequencies, power_spectrum, center_freq_mhz, output_file=None):
         """Plot helper (:114-134).  matplotlib is optional; without it this raises ImportError."""
         import matplotlib
-        matplotlib.use("Agg")
+        if output_file and not plt_backend_is_set():
+            matplotlib.use("Agg")                              # headless file output only; never override a caller's backend
         import matplotlib.pyplot as plt
         plt.figure(figsize=(12, 6))
         plt.plot(frequencies, power_spectrum)

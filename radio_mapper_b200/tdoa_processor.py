@@ -445,10 +445,12 @@ class TDoAProcessor:
 
     def triangulate_iq(self, iq_u8, buoy_ids: Sequence[str], sample_rate: float = 2048000,
                        frequency_mhz: float = 0.0, signal_type: str = "unknown",
-                       max_lag: Optional[int] = None, robust: bool = False) -> List[Optional[TriangulationResult]]:
+                       max_lag: Optional[int] = None, robust: bool = False, device=None,
+                       distributed: bool = False) -> List[Optional[TriangulationResult]]:
         """correlate_iq + host multilateration, one result (or None) per window.  robust=True uses
-        `triangulate_position_robust` instead of the reference's BFGS."""
-        meas = self.correlate_iq(iq_u8, buoy_ids, sample_rate, frequency_mhz, max_lag=max_lag)
+        `triangulate_position_robust` instead of the reference's BFGS; device / distributed as in correlate_iq."""
+        meas = self.correlate_iq(iq_u8, buoy_ids, sample_rate, frequency_mhz, max_lag=max_lag, device=device,
+                                 distributed=distributed)
         solve = self.hyperbolic_positioner.triangulate_position_robust if robust else \
             self.hyperbolic_positioner.triangulate_position
         per_window = len(meas) // max(1, (len(buoy_ids) * (len(buoy_ids) - 1)) // 2)

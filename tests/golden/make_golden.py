@@ -191,6 +191,64 @@ def main():
     )
     with open(os.path.join(HERE, "tdoa.json"), "w") as f:
         json.dump(tdoa_json, f, indent=1)
+
+    # ---- (b) the drop-in surface: signatures and dataclass fields of the reference, as strings ----
+    import dataclasses
+    import inspect
+
+    def sig(obj):
+        sg = inspect.signature(obj)
+        return {"text": str(sg),
+                "params": [[q.name, q.kind.name, None if q.default is inspect.Parameter.empty else repr(q.default)]
+                           for q in sg.parameters.values()]}
+
+    def fields(cls):
+        return [[f.name, None if f.default is dataclasses.MISSING else repr(f.default)] for f in dataclasses.fields(cls)]
+
+    surface = {
+        "buoy_node": {
+            "SignalDetector.__init__": sig(ref_buoy.SignalDetector.__init__),
+            "SignalDetector._detect_real_signals": sig(ref_buoy.SignalDetector._detect_real_signals),
+            "SignalDetector._classify_signal": sig(ref_buoy.SignalDetector._classify_signal),
+            "SignalDetector._fallback_signal_detection": sig(ref_buoy.SignalDetector._fallback_signal_detection),
+            "GPSTimeSource.__init__": sig(ref_buoy.GPSTimeSource.__init__),
+            "GPSTimeSource.get_precise_timestamp": sig(ref_buoy.GPSTimeSource.get_precise_timestamp),
+            "GPSTimeSource.get_position": sig(ref_buoy.GPSTimeSource.get_position),
+            "SignalDetection": fields(ref_buoy.SignalDetection),
+        },
+        "iq_stream_client": {
+            "RealTimeSDRCapture.__init__": sig(ref_stream.RealTimeSDRCapture.__init__),
+            "RealTimeSDRCapture.read_iq_samples": sig(ref_stream.RealTimeSDRCapture.read_iq_samples),
+            "RealTimeSDRCapture.start_capture": sig(ref_stream.RealTimeSDRCapture.start_capture),
+            "RealTimeSDRCapture.stop_capture": sig(ref_stream.RealTimeSDRCapture.stop_capture),
+            "SignalDetector.__init__": sig(ref_stream.SignalDetector.__init__),
+            "SignalDetector.detect_signals": sig(ref_stream.SignalDetector.detect_signals),
+            "SignalDetector._estimate_bandwidth": sig(ref_stream.SignalDetector._estimate_bandwidth),
+            "SignalDetector._classify_signal": sig(ref_stream.SignalDetector._classify_signal),
+            "SignalDetector._extract_signal_samples": sig(ref_stream.SignalDetector._extract_signal_samples),
+            "SignalDetection": fields(ref_stream.SignalDetection),
+        },
+        "tdoa_processor": {
+            "TDoAProcessor.__init__": sig(T.TDoAProcessor.__init__),
+            "TDoAProcessor.register_buoy": sig(T.TDoAProcessor.register_buoy),
+            "TDoAProcessor.process_signal_detections": sig(T.TDoAProcessor.process_signal_detections),
+            "TDoAProcessor._group_by_frequency": sig(T.TDoAProcessor._group_by_frequency),
+            "TDoAProcessor._filter_by_time_window": sig(T.TDoAProcessor._filter_by_time_window),
+            "TDoAProcessor.get_buoy_network_status": sig(T.TDoAProcessor.get_buoy_network_status),
+            "TDoACalculator.calculate_tdoa_measurements": sig(T.TDoACalculator.calculate_tdoa_measurements),
+            "HyperbolicPositioning.triangulate_position": sig(T.HyperbolicPositioning.triangulate_position),
+            "GeodeticCalculator.lat_lng_to_xyz": sig(T.GeodeticCalculator.lat_lng_to_xyz),
+            "GeodeticCalculator.xyz_to_lat_lng": sig(T.GeodeticCalculator.xyz_to_lat_lng),
+            "GeodeticCalculator.distance_3d": sig(T.GeodeticCalculator.distance_3d),
+            "GeodeticCalculator.bearing_distance": sig(T.GeodeticCalculator.bearing_distance),
+            "BuoyPosition": fields(T.BuoyPosition), "SignalDetection": fields(T.SignalDetection),
+            "TDoAMeasurement": fields(T.TDoAMeasurement), "TriangulationResult": fields(T.TriangulationResult),
+        },
+        "signal_analyzer": {name: sig(getattr(ref_sa, name)) for name in
+                            ("load_iq_data", "analyze_spectrum", "calculate_signal_stats", "plot_spectrum", "analyze_iq_file")},
+    }
+    with open(os.path.join(HERE, "signatures.json"), "w") as f:
+        json.dump(surface, f, indent=1)
     print("golden vectors written to", HERE)
     print("  buoy detections:", len(buoy_json), " stream detections:", len(stream_json),
           " tdoa measurements:", len(meas), " solve:", tdoa_json["solve"]["result"])

@@ -185,7 +185,7 @@ def test_xcorr_one_pass_windowed_search(rmx, log_n, max_lag):
 
 
 @pytest.mark.parametrize("log_n", [17, 20, 22])
-def test_kernel_variants_agree(rmx, monkeypatch, log_n):
+def test_kernel_variants_agree(rmx, log_n):
     """The TMA-fed arg-max pass, the X_i-stationary row pass and the twiddle placement are
     re-arrangements of the same arithmetic: every variant must return the oracle's lags, and peaks /
     sub-sample offsets inside the north_star tolerances of each other (plans 32x4096, 256x4096, 1024x8192)."""
@@ -194,21 +194,20 @@ def test_kernel_variants_agree(rmx, monkeypatch, log_n):
     want = np.array([delays[j] - delays[i] for i, j in oracle.pair_list(5)])
     pairs = _cuda(rmx.pair_table(5))
     results = {}
-    for name, env in [("default", {}), ("no_tma", {"RMX_NO_TMA": "1"}), ("no_pair_run", {"RMX_NO_PAIR_RUN": "1"}),
-                      ("twiddle_in_col", {"RMX_TWIDDLE_IN_COL": "1"}),
-                      ("all_off", {"RMX_NO_TMA": "1", "RMX_NO_PAIR_RUN": "1", "RMX_TWIDDLE_IN_COL": "1"})]:
-        for k in ("RMX_NO_TMA", "RMX_NO_PAIR_RUN", "RMX_TWIDDLE_IN_COL"):
-            monkeypatch.delenv(k, raising=False)
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        plan = rmx.Plan(5, n)
+    from radio_mapper_b200 import _native as nat
+    for name, flags, options in [("default", 0, {}), ("no_tma", nat.PLAN_NO_TMA, {}), ("no_pair_run", nat.PLAN_NO_PAIR_RUN, {}),
+                                 ("twiddle_in_col", nat.PLAN_TWIDDLE_IN_COL, {}),
+                                 ("no_prefetch", 0, {"pair_prefetch": 0}), ("run16", 0, {"pair_run": 16}),
+                                 ("fwd_groups", 0, {"fwd_group_bytes": 3 * 8 * 2 * n}),
+                                 ("all_off", nat.PLAN_NO_TMA | nat.PLAN_NO_PAIR_RUN | nat.PLAN_TWIDDLE_IN_COL, {"pair_prefetch": 0})]:
+        plan = rmx.Plan(5, n, flags=flags, options=options)
         S = plan.forward(_cuda(iq))
         results[name] = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, pairs)).copy()
         full = plan.xcorr_full(S, pairs[:2].contiguous()).cpu().numpy()
         results[name + "_full"] = full
     ref = results["default"]
     assert np.array_equal(ref["lag"], want)
-    for name in ("no_tma", "no_pair_run", "twiddle_in_col", "all_off"):
+    for name in ("no_tma", "no_pair_run", "twiddle_in_col", "no_prefetch", "run16", "fwd_groups", "all_off"):
         _check_records(results[name], ref)
         a, b = results[name + "_full"], results["default_full"]
         assert np.linalg.norm(a - b) <= 2e-6 * np.linalg.norm(b), name
@@ -315,6 +314,72 @@ def test_cfg5_size_known_delays(rmx):
     """N = 2^26 (L = 2^27, three passes): 3 buoys of the 8 to bound memory and time."""
     plan = _delays_ok(rmx, 3, 26, 505)
     assert len(plan.pass_lengths) == 3
+
+
+def _oracle_subset_parity(rmx, n_buoys, log_samples, seed, subset, expect_passes):
+    """All pairs of all `n_buoys` buoys on the GPU at the BASELINE plan size; the pairs among the buoys in `subset`
+    are also run through the CPU oracle on the same bytes: lags bit-exact, peak within 1e-4 relative, sub-sample
+    offset within 1e-3 samples (north_star tolerances) -- plus every GPU lag against the generator's delay."""
+    import torch
+    n = 1 << log_samples
+    iq, delays = synth.delayed_buoys_torch(seed, n_buoys, 1, n, torch.device("cuda"))
+    plan = rmx.Plan(n_buoys, n)
+    assert plan.pass_lengths == expect_passes
+    pairs_h = rmx.pair_table(n_buoys)
+    got = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(plan.forward(iq[:, 0, :]), _cuda(pairs_h)))
+    assert np.array_equal(got["lag"], delays[0, pairs_h[:, 1]] - delays[0, pairs_h[:, 0]])
+    host = iq[list(subset), 0, :].cpu().numpy()
+    ref = oracle.xcorr_pairs_peak(host)                       # pairs of the subset, i<j in subset order
+    index = {(int(i), int(j)): k for k, (i, j) in enumerate(pairs_h)}
+    sel = [index[(subset[a], subset[b])] for a, b in oracle.pair_list(len(subset))]
+    _check_records(got[sel], ref)
+    return got, ref
+
+
+def test_cfg3_plan_matches_oracle(rmx):
+    """BASELINE config 3 as benchmarked: 16 buoys / 120 pairs / N = 2^22, plan 1024 x 8192.  Six pairs (four
+    buoys) against scipy.signal.correlate on the CPU."""
+    _oracle_subset_parity(rmx, 16, 22, 3303, (0, 5, 10, 15), [1024, 8192])
+
+
+def test_cfg4_plan_matches_oracle(rmx):
+    """BASELINE config 4: 64 buoys / 2016 pairs / N = 2^20, plan 512 x 4096 (X_i-stationary row pass with the
+    bulk-copy prefetch, TMA arg-max pass).  Six pairs drawn across the 64 buoys against the oracle."""
+    _oracle_subset_parity(rmx, 64, 20, 4404, (0, 17, 42, 63), [512, 4096])
+
+
+def test_cfg5_plan_matches_oracle(rmx):
+    """BASELINE config 5: ALL 8 buoys / 28 pairs at N = 2^26 (three-pass plan 128 x 256 x 4096): every lag against
+    the generator, and one pair against the oracle (a 2^27-point scipy correlation takes ~1 min of CPU)."""
+    got, ref = _oracle_subset_parity(rmx, 8, 26, 5505, (2, 5), [128, 256, 4096])
+    assert len(got) == 28 and len(ref) == 1
+
+
+@pytest.mark.parametrize("n_buoys,world,log_samples", [(16, 3, 20), (64, 8, 16), (5, 8, 17)])
+def test_tiled_records_identical_to_untiled(rmx, n_buoys, world, log_samples):
+    """sharding.tile_pairs deals blocks of the pair matrix to ranks; a rank transforms only its tile's buoys and
+    correlates only its pairs (Correlator.run_device_tile).  Running EVERY tile on one GPU and assembling the
+    records by global pair index must reproduce Correlator.run_device byte for byte: same kernels, same
+    spectra, only the launch grouping differs."""
+    import torch
+    from radio_mapper_b200 import sharding
+    from radio_mapper_b200.correlator import Correlator
+    n = 1 << log_samples
+    iq, delays = synth.delayed_buoys_torch(90 + n_buoys, n_buoys, 2, n, torch.device("cuda"))
+    cor = Correlator(n_buoys, n)
+    full, energy = cor.run_device(iq, [0, 1])
+    full = full.clone()
+    tiles = sharding.tile_pairs(n_buoys, world)
+    assert sorted(np.concatenate([t["global_index"] for t in tiles]).tolist()) == list(range(cor.n_pairs))
+    assembled = torch.full_like(full, -1)
+    for t in tiles:
+        rec, en = cor.run_device_tile(iq, [0, 1], t)
+        assert torch.equal(en, energy)
+        if len(t["global_index"]):
+            assembled[:, torch.from_numpy(t["global_index"]).cuda()] = rec
+    assert torch.equal(assembled, full)
+    want = np.stack([delays[:, j] - delays[:, i] for i, j in cor.pairs_host], axis=1)
+    assert np.array_equal(full.cpu().numpy()[..., 0], want)
 
 
 def test_cfg1_exact_reference_case(rmx):

@@ -100,18 +100,25 @@ def test_welch_parity(rmx, nperseg, n_seg):
 
 
 @pytest.mark.parametrize("nperseg", [16384, 32768, 65536])
-def test_welch_cluster_kernel_matches_two_pass(rmx, monkeypatch, nperseg):
+def test_welch_cluster_kernel_matches_two_pass(rmx, nperseg):
     """nperseg = C*8192 runs as ONE kernel on a cluster of C CTAs (segment held in distributed shared
-    memory); RMX_NO_WELCH_CLUSTER=1 takes the two-pass path through HBM.  Same transform, different
-    factorisation: the PSDs agree to float32 rounding."""
+    memory); a plan created with RMX_PLAN_NO_WELCH_CLUSTER takes the two-pass path through HBM, and so does an
+    input pointer that is not 8-byte aligned (the engine then sizes the workspace for many segments in
+    flight).  Same transform, different factorisation: the PSDs agree to float32 rounding."""
+    from radio_mapper_b200 import _native as nat
     n_seg = 45
     iq, _ = synth.welch_stream(11, n_seg, nperseg)
-    plan = rmx.Plan(n_seg, nperseg, nperseg)
-    monkeypatch.delenv("RMX_NO_WELCH_CLUSTER", raising=False)
-    a = plan.welch_psd(_cuda(iq), 2.4e6).cpu().numpy()
-    monkeypatch.setenv("RMX_NO_WELCH_CLUSTER", "1")
-    b = plan.welch_psd(_cuda(iq), 2.4e6).cpu().numpy()
+    a = rmx.Plan(n_seg, nperseg, nperseg, flags=0).welch_psd(_cuda(iq), 2.4e6).cpu().numpy()
+    b = rmx.Plan(n_seg, nperseg, nperseg, flags=nat.PLAN_NO_WELCH_CLUSTER).welch_psd(_cuda(iq), 2.4e6).cpu().numpy()
     assert np.max(np.abs(a / b - 1)) < 2e-5
+    # unaligned view (2 bytes into a larger buffer): two-pass fallback, same numbers as the forced two-pass plan
+    import torch
+    big = torch.empty(iq.size + 2, dtype=torch.uint8, device="cuda")
+    big[2:].copy_(torch.from_numpy(iq.reshape(-1)))
+    plan = rmx.Plan(n_seg, nperseg, nperseg, flags=0)
+    c = plan.welch_psd(big[2:], 2.4e6).cpu().numpy()
+    assert plan._workspace.numel() > 8 * nperseg * min(n_seg, 8)        # sized for many segments, not one
+    assert np.max(np.abs(c / b - 1)) < 2e-6                            # same kernels; only the atomicAdd order differs
 
 
 def test_cfg2_size_welch_against_oracle_and_parseval(rmx):
@@ -191,12 +198,68 @@ def test_load_iq_data_roundtrip(tmp_path, golden_dir):
     assert fs == 2048000 and np.array_equal(x.view(np.uint32), g["x_file"].view(np.uint32))
     bad, none = sa.SignalAnalyzer(verbose=False).load_iq_data(str(tmp_path / "missing.bin"))
     assert bad is None and none is None                       # same error contract as the reference
+    odd = tmp_path / "odd.bin"
+    g["raw"][:-1].tofile(odd)                                 # odd byte count: the reference's I + 1j*Q raises -> (None, None)
+    bad, none = sa.SignalAnalyzer(verbose=False).load_iq_data(str(odd))
+    assert bad is None and none is None
 
 
-def test_buoy_detector_matches_reference_golden(golden_dir):
-    """BuoySignalDetector vs the detections the reference's _detect_real_signals produced on the
-    same bytes (golden), aligned by FFT bin through the oracle (itself pinned to that golden)."""
-    from radio_mapper_b200.detectors import BuoySignalDetector
+def _explained_peak_flips(diff, p, height, distance, tol=2e-3):
+    """Which bins of `diff` (symmetric difference of two find_peaks(height=, distance=) results computed from dB
+    spectra that agree to tol/2) can legitimately differ?  A bin may flip when
+      (a) its height is within tol of the height threshold,
+      (b) it ties an immediate neighbour within tol (strict-local-maximum test flips),
+      (c) a candidate within `distance` bins has a height within tol of it (the greedy rule's priority flips), or
+      (d) a bin within `distance` of it is itself an explained flip (its removal / survival cascades).
+    Returns the set of explained bins; the caller asserts it equals `diff`."""
+    n = len(p)
+    diff = set(map(int, diff))
+    explained = set()
+    for k in diff:
+        near_height = abs(p[k] - height) <= tol
+        near_tie = 0 < k < n - 1 and min(abs(p[k] - p[k - 1]), abs(p[k] - p[k + 1])) <= tol
+        lo, hi = max(0, k - distance + 1), min(n, k + distance)
+        near_priority = any(j != k and abs(p[j] - p[k]) <= tol for j in range(lo, hi))
+        if near_height or near_tie or near_priority:
+            explained.add(k)
+    changed = True
+    while changed:
+        changed = False
+        for k in diff - explained:
+            if any(abs(j - k) < distance for j in explained):
+                explained.add(k)
+                changed = True
+    return explained
+
+
+def _rounds_differently(value, decimals, err):
+    """True when an error of `err` on `value` can change round(value, decimals)."""
+    scaled = value * 10.0 ** decimals
+    return abs(scaled - np.floor(scaled) - 0.5) <= err * 10.0 ** decimals + 1e-9
+
+
+def _check_buoy_detections(got_by_bin, want_by_bin, p):
+    """Every difference from the reference's golden detections must be PROVEN threshold-adjacent: no percentage
+    allowances.  p = oracle dB spectrum of the block (the GPU's agrees to 1e-3 dB, test_spectrum_db_parity)."""
+    med = float(np.median(p))
+    diff = set(want_by_bin) ^ set(got_by_bin)
+    peak_flips = _explained_peak_flips(diff, p, -70.0, 10)
+    for k in diff - peak_flips:
+        # not a find_peaks flip: then the confidence must sit on the 0.3 gate (snr within 2e-3 dB of 6 dB)
+        assert abs((p[k] - med) / 20.0 - 0.3) <= 1e-4, (k, p[k], med)
+    for k in set(want_by_bin) & set(got_by_bin):
+        d, w = got_by_bin[k], want_by_bin[k]
+        assert d.frequency_mhz == w["frequency_mhz"] and d.signal_type == w["signal_type"]
+        if float(d.signal_strength_dbm) != w["signal_strength_dbm"]:
+            assert abs(float(d.signal_strength_dbm) - w["signal_strength_dbm"]) <= 0.1001
+            assert _rounds_differently(float(p[k]), 1, 1e-3), (k, p[k])                 # 1-decimal rounding boundary
+        if float(d.confidence) != w["confidence"]:
+            assert abs(float(d.confidence) - w["confidence"]) <= 0.0101
+            assert _rounds_differently(min(max((float(p[k]) - med) / 20.0, 0.0), 1.0), 2, 2e-3 / 20.0), (k, p[k])
+    return len(diff)
+
+
+def _buoy_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "buoy_detect.npz"))
     with open(os.path.join(golden_dir, "buoy_detect.json")) as f:
         want = json.load(f)
@@ -205,46 +268,127 @@ def test_buoy_detector_matches_reference_golden(golden_dir):
     p = oracle.spectrum_db(oracle.forward_fft(x))
     ora = oracle.score_peaks_buoy(p, oracle.detect_peaks_fixed(p), oracle.freq_axis_hz(len(x), fs, fc_hz), fc_hz)
     assert len(ora) == len(want)
-    want_by_bin = {o["index"]: w for o, w in zip(ora, want)}
+    return g, p, {o["index"]: w for o, w in zip(ora, want)}
+
+
+def test_buoy_detector_matches_reference_golden(golden_dir):
+    """BuoySignalDetector vs the detections the reference's _detect_real_signals produced on the
+    same bytes (golden), aligned by FFT bin through the oracle (itself pinned to that golden)."""
+    from radio_mapper_b200.detectors import BuoySignalDetector
+    g, p, want_by_bin = _buoy_golden(golden_dir)
     bins, got = BuoySignalDetector("BUOY_T", 35.4676, -97.5164).detect_block_indexed(g["iq"], float(g["center_mhz"]))
-    got_by_bin = dict(zip(bins, got))
-    # the detection sets differ only where confidence sits on the 0.3 gate (snr within 1e-3 dB of 6 dB)
-    for k in set(want_by_bin) ^ set(got_by_bin):
-        assert abs((p[k] - np.median(p)) / 20.0 - 0.3) < 1e-4, k
-    exact = 0
-    common = set(want_by_bin) & set(got_by_bin)
-    assert len(common) >= len(want) - 3
-    for k in common:
-        d, w = got_by_bin[k], want_by_bin[k]
-        assert d.frequency_mhz == w["frequency_mhz"] and d.signal_type == w["signal_type"]
-        assert abs(float(d.signal_strength_dbm) - w["signal_strength_dbm"]) <= 0.1001      # 1-decimal rounding
-        assert abs(float(d.confidence) - w["confidence"]) <= 0.0101                         # 2-decimal rounding
-        exact += (float(d.signal_strength_dbm) == w["signal_strength_dbm"]) and (float(d.confidence) == w["confidence"])
-    assert exact >= 0.97 * len(want)          # rounding-boundary flips only
+    _check_buoy_detections(dict(zip(bins, got)), want_by_bin, p)
 
 
-def test_stream_detector_matches_reference_golden(golden_dir):
-    from radio_mapper_b200.detectors import StreamSignalDetector
-    g = np.load(os.path.join(golden_dir, "stream_detect.npz"))
-    with open(os.path.join(golden_dir, "stream_detect.json")) as f:
-        want = json.load(f)
-    fs, fc = int(g["sample_rate"]), float(g["center_hz"])
-    x = oracle.unpack_cu8(g["iq"])
-    p = oracle.spectrum_db(oracle.forward_fft(x))
-    peaks = oracle.detect_peaks_fixed(p)
-    assert len(peaks) == len(want)
-    want_by_bin = dict(zip(map(int, peaks), want))
-    bins, got = StreamSignalDetector("NODE_T").detect_signals_indexed(x, fc)
-    got_by_bin = dict(zip(bins, got))
-    assert len(set(want_by_bin) ^ set(got_by_bin)) <= 2
-    same_bw = 0
+def test_buoy_node_module_matches_reference_golden(golden_dir):
+    """The drop-in `buoy_node.SignalDetector._detect_real_signals(center_freq_mhz)` with the capture step injected
+    (the golden was recorded from the reference with rtl_sdr mocked by the same bytes)."""
+    import buoy_node as bn
+    g, p, want_by_bin = _buoy_golden(golden_dir)
+    gps = bn.GPSTimeSource()
+    gps.gps_locked, gps.lat, gps.lng = True, 35.4676, -97.5164
+    gps.get_precise_timestamp = lambda: ("2025-01-01T00:00:00+00:00", 1735689600000000000)
+    seen = []
+
+    def capture(fc_hz, fs, n):
+        seen.append((fc_hz, fs, n))
+        return g["iq"].tobytes()
+
+    det = bn.SignalDetector("BUOY_T", gps, capture=capture)
+    got = det._detect_real_signals(float(g["center_mhz"]))
+    assert seen == [(121500000, 2048000, 16384)]                       # the reference's capture parameters (:362-365)
+    assert all(isinstance(d, bn.SignalDetection) and d.buoy_id == "BUOY_T" and d.lat == 35.4676 and d.lng == -97.5164
+               and d.timestamp_utc == "2025-01-01T00:00:00+00:00" and d.gps_timestamp_ns == 1735689600000000000
+               and d.iq_sample_file is None for d in got)
+    # align by frequency: frequency_mhz is round(f, 3) of the bin frequency, unique per bin at 62.5 Hz spacing? no --
+    # several bins share a rounded MHz value, so align by order instead: both lists are in increasing bin order
+    fs, fc_hz = int(g["sample_rate"]), int(float(g["center_mhz"]) * 1e6)
+    from radio_mapper_b200.detectors import BuoySignalDetector
+    bins, ref_objs = BuoySignalDetector("BUOY_T", 35.4676, -97.5164).detect_block_indexed(g["iq"], float(g["center_mhz"]))
+    assert len(bins) == len(got)
+    for d, r in zip(got, ref_objs):
+        assert (d.frequency_mhz, d.signal_strength_dbm, d.confidence, d.signal_type) == \
+               (r.frequency_mhz, r.signal_strength_dbm, r.confidence, r.signal_type)
+    _check_buoy_detections(dict(zip(bins, got)), want_by_bin, p)
+
+
+def _bandwidth_walk_is_marginal(p, k, tol=2e-3):
+    """The -3 dB walk of iq_stream_client.py:254-278 from peak k compares p[bin] > p[k] - 3 bin by bin; its result
+    can differ between two spectra that agree to tol/2 only if some comparison on the walk is within tol."""
+    thr = p[k] - 3.0
+    last = len(p) - 1
+    left = right = int(k)
+    marginal = False
+    while left > 0 and p[left] > thr:
+        marginal |= abs(p[left] - thr) <= tol
+        left -= 1
+    marginal |= abs(p[left] - thr) <= tol
+    while right < last and p[right] > thr:
+        marginal |= abs(p[right] - thr) <= tol
+        right += 1
+    marginal |= abs(p[right] - thr) <= tol
+    return marginal
+
+
+def _check_stream_detections(got_by_bin, want_by_bin, p):
+    diff = set(want_by_bin) ^ set(got_by_bin)
+    assert _explained_peak_flips(diff, p, -70.0, 10) == diff, sorted(diff)
     for k in set(want_by_bin) & set(got_by_bin):
         d, w = got_by_bin[k], want_by_bin[k]
         assert d.frequency_mhz == w["frequency_mhz"] and d.signal_type == w["signal_type"]
         assert abs(float(d.signal_strength_dbm) - w["signal_strength_dbm"]) <= 1e-3
         assert abs(float(d.confidence) - w["confidence"]) <= 1e-4
-        same_bw += d.bandwidth_hz == w["bandwidth_hz"]
-    assert same_bw >= 0.98 * len(want)
+        if d.bandwidth_hz != w["bandwidth_hz"]:
+            assert _bandwidth_walk_is_marginal(p, k), (k, d.bandwidth_hz, w["bandwidth_hz"])
+
+
+def _stream_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "stream_detect.npz"))
+    with open(os.path.join(golden_dir, "stream_detect.json")) as f:
+        want = json.load(f)
+    x = oracle.unpack_cu8(g["iq"])
+    p = oracle.spectrum_db(oracle.forward_fft(x))
+    peaks = oracle.detect_peaks_fixed(p)
+    assert len(peaks) == len(want)
+    return g, x, p, dict(zip(map(int, peaks), want))
+
+
+def test_stream_detector_matches_reference_golden(golden_dir):
+    from radio_mapper_b200.detectors import StreamSignalDetector
+    g, x, p, want_by_bin = _stream_golden(golden_dir)
+    bins, got = StreamSignalDetector("NODE_T").detect_signals_indexed(x, float(g["center_hz"]))
+    _check_stream_detections(dict(zip(bins, got)), want_by_bin, p)
+
+
+def test_iq_stream_client_module_matches_reference_golden(golden_dir):
+    """The drop-in `iq_stream_client`: read_iq_samples on a mocked rtl_sdr pipe is bit-exact with the reference's
+    (golden unpack.npz x_pipe), and SignalDetector.detect_signals reproduces the reference's detections."""
+    import io
+    import iq_stream_client as sc
+
+    class _Proc:
+        def __init__(self, data):
+            self.stdout = io.BytesIO(data)
+
+    u = np.load(os.path.join(golden_dir, "unpack.npz"))
+    cap = sc.RealTimeSDRCapture()
+    cap.running, cap.capture_process = True, _Proc(u["raw"].tobytes())
+    x = cap.read_iq_samples(4096)
+    assert x.dtype == np.complex64 and np.array_equal(x.view(np.uint32), u["x_pipe"].view(np.uint32))
+    assert cap.read_iq_samples(4096) is None                           # pipe exhausted: short read -> None
+
+    g, xs, p, want_by_bin = _stream_golden(golden_dir)
+    cap.capture_process = _Proc(g["iq"].tobytes())
+    block = cap.read_iq_samples(len(g["iq"]) // 2)
+    assert np.array_equal(block.view(np.uint32), xs.view(np.uint32))
+    det = sc.SignalDetector("NODE_T")
+    got = det.detect_signals(block, float(g["center_hz"]))
+    assert all(isinstance(d, sc.SignalDetection) and d.node_id == "NODE_T" and d.detection_method == "fft_peak"
+               and len(d.iq_samples) == 256 for d in got)
+    bins, _ = det.detect_signals_indexed(block, float(g["center_hz"]))
+    assert len(bins) == len(got)
+    _check_stream_detections(dict(zip(bins, got)), want_by_bin, p)
+    assert det.detect_signals(np.zeros(0, np.complex64), 100e6) == []  # errors are logged and yield [] (:249-252)
 
 
 def test_non_power_of_two_blocks_and_files(tmp_path):
@@ -259,7 +403,8 @@ def test_non_power_of_two_blocks_and_files(tmp_path):
     peaks = oracle.detect_peaks_fixed(p)
     want = oracle.score_peaks_stream(p, peaks, oracle.freq_axis_hz(n, 2048000, 100e6), 2048000)
     kbins, got = StreamSignalDetector("N").detect_signals_indexed(x, 100e6)
-    assert len(set(kbins) ^ set(map(int, peaks))) <= 2
+    diff = set(kbins) ^ set(map(int, peaks))
+    assert _explained_peak_flips(diff, p, -70.0, 10, tol=4e-3) == diff, sorted(diff)
     wb = {w["index"]: w for w in want}
     for k, d in zip(kbins, got):
         if k in wb:
@@ -269,7 +414,10 @@ def test_non_power_of_two_blocks_and_files(tmp_path):
     fc_hz = int(121.5 * 1e6)
     ora = oracle.score_peaks_buoy(p, peaks, oracle.freq_axis_hz(n, 2048000, fc_hz), fc_hz)
     bbins, bgot = BuoySignalDetector("B").detect_block_indexed(iq, 121.5)
-    assert len(set(bbins) ^ {o["index"] for o in ora}) <= max(2, len(ora) // 100)
+    diff = set(bbins) ^ {o["index"] for o in ora}
+    flips = _explained_peak_flips(diff, p, -70.0, 10, tol=4e-3)
+    for k in diff - flips:                                     # otherwise the confidence sits on the 0.3 gate
+        assert abs((p[k] - np.median(p)) / 20.0 - 0.3) <= 2e-4, k
     # whole-file analysis of a capture whose length is not a power of two
     path = tmp_path / "iq_capture_100.0MHz_20250101.bin"
     big, _ = synth.tones_block(78, 250_000)

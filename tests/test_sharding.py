@@ -112,10 +112,19 @@ def _tile_worker(rank, world, port, n_buoys, q):
     try:
         n_pairs = n_buoys * (n_buoys - 1) // 2
         full = torch.arange(2 * n_pairs * 4, dtype=torch.int32).reshape(2, n_pairs, 4)
-        tiles = sharding.tile_pairs(n_buoys, world)
-        mine = full[:, torch.from_numpy(tiles[rank]["global_index"])].contiguous()
-        got = sharding.gather_tiled_records(mine, tiles, n_pairs, world)
-        q.put((rank, bool(torch.equal(got, full))))
+        ok = True
+        # several tilings in one process, some built and dropped on the fly: the permutation cache is keyed by
+        # CONTENT, so a recycled id() or an equal padded width can never return a stale table
+        for nb in (n_buoys, n_buoys + 1, n_buoys, n_buoys + 2):
+            n_pairs = nb * (nb - 1) // 2
+            full = torch.arange(2 * n_pairs * 4, dtype=torch.int32).reshape(2, n_pairs, 4)
+            for tiles in (sharding.tile_pairs(nb, world), sharding.tiles_for(nb, world)):
+                mine = full[:, torch.from_numpy(tiles[rank]["global_index"])].contiguous()
+                got = sharding.gather_tiled_records(mine, tiles, n_pairs, world)
+                ok = ok and bool(torch.equal(got, full))
+                del tiles
+        assert sharding.tiles_for(n_buoys, world) is sharding.tiles_for(n_buoys, world)
+        q.put((rank, ok))
     finally:
         dist.destroy_process_group()
 
