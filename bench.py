@@ -11,6 +11,9 @@ pair-samples/s = pairs * samples_per_window * windows / time, whole job over all
 One JSON line is printed by rank 0 (see the contract in the task statement).  For N > 1 it is
 launched by torchrun, one rank per GPU; each rank processes its own windows (weak scaling)
 and the 16-byte peak records are all-gathered over NCCL inside the timed step.
+
+The same line carries `pair_sharded`: BASELINE config 4 as worded (64 buoys / 2016 pairs, ONE 2^20-sample
+window whose pairs are sharded over the N ranks, strong scaling) with its own 1-GPU reference time.
 """
 import argparse
 import json
@@ -48,12 +51,21 @@ def algorithmic_bytes(B, P, N, L):
     return B * (2 * N + 8 * L) + P * (16 * L + 16), B * (2 * N + 8 * L), P * (16 * L + 16)
 
 
+def traffic_table():
+    """Per-unit DRAM traffic of the pair-stage kernels from the newest committed ncu --set full capture."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            with open(path) as f:
+                return json.load(f)
+    raise FileNotFoundError("no profiles/r0*_traffic.json")
+
+
 def measured_traffic(workload, B, P, L):
     """DRAM bytes per launch of the correlate+peak stage, scaled from the ncu --set full capture recorded in
     profiles/r01_traffic.json (per-unit ratios measured on the same kernels at the same FFT length)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            t = json.load(f)[workload]
+        t = traffic_table()[workload]
         unit = 8 * L
         return int(unit * (B * t["pair_pass_read_per_buoy_unit8L"] + P * (t["pair_pass_write_per_pair_unit8L"] +
                                                                           t["argmax_pass_read_per_pair_unit8L"]))), t["source"]
@@ -154,6 +166,71 @@ def cpu_sample_run(iq_sample, threads):
     return time.perf_counter() - t0, len(pairs), res
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    import platform
+    return platform.processor() or platform.machine()
+
+
+def cpu_baseline_cfg1():
+    """the oracle on config 1 EXACTLY (3 buoys, 2.048 Msps cu8, 1 s window = 2 048 000 samples,
+    3 pairs, seeded synthetic input), in this process on this box's host cores -- once as the reference would run
+    it (scipy default workers=1) and once under scipy.fft.set_workers(os.cpu_count()); per-stage milliseconds,
+    CPU model and library versions in the record."""
+    import numpy
+    import scipy
+    import scipy.fft
+    import oracle
+    from radio_mapper_b200 import synth
+    B, N = 3, 2_048_000
+    iq, delays, _ = synth.delayed_buoys(1000, B, N, sample_rate=2_048_000)
+    pairs = oracle.pair_list(B)
+
+    def once():
+        st = {"unpack_ms": 0.0, "correlate_ms": 0.0, "argmax_ms": 0.0}
+        t0 = time.perf_counter()
+        x = [oracle.unpack_cu8(row) for row in iq]
+        t1 = time.perf_counter()
+        st["unpack_ms"] = 1e3 * (t1 - t0)
+        lags = []
+        for i, j in pairs:
+            ta = time.perf_counter()
+            c, lg = oracle.xcorr_full(x[i], x[j])
+            tb = time.perf_counter()
+            lags.append(oracle.peak_lag(c, lg)[0])
+            tc = time.perf_counter()
+            st["correlate_ms"] += 1e3 * (tb - ta)
+            st["argmax_ms"] += 1e3 * (tc - tb)
+        st["total_ms"] = 1e3 * (time.perf_counter() - t0)
+        return st, lags
+
+    def best_of(k):
+        runs = [once() for _ in range(k)]
+        st, lags = min(runs, key=lambda r: r[0]["total_ms"])
+        return {k2: round(v, 2) for k2, v in st.items()}, lags
+
+    cores = os.cpu_count() or 1
+    st1, lags1 = best_of(2)
+    with scipy.fft.set_workers(cores):
+        stn, lagsn = best_of(2)
+    want = [int(delays[j] - delays[i]) for i, j in pairs]
+    ps = len(pairs) * N
+    return {"value": ps / (st1["total_ms"] * 1e-3), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "BASELINE config 1 exactly: 3 buoys x 2 048 000 samples, 3 pairs; numpy unpack + "
+                      "scipy.signal.correlate('full','fft') + argmax/parabolic; best of 2 runs, scipy workers=1",
+            "stages_ms": st1,
+            "all_workers": {"value": ps / (stn["total_ms"] * 1e-3), "workers": cores, "stages_ms": stn,
+                            "note": "the same run under scipy.fft.set_workers(os.cpu_count())"},
+            "host_cpus": cores, "cpu_model": cpu_model(), "numpy": numpy.__version__, "scipy": scipy.__version__,
+            "lags_match_known_delays": lags1 == want and lagsn == want}, iq, lags1
+
+
 def run_reference(args, wl):
     """`--impl reference`: the reference's CPU arithmetic (oracle port: numpy unpack +
     scipy.signal.correlate + argmax; the reference has no compiled implementation of this
@@ -188,6 +265,94 @@ def run_reference(args, wl):
         "e2e": {"value": ps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def welch_roofline(n_seg, nperseg, ms, clocks):
+    """fp32 roofline of the Welch PSD (compute-bound): flops = W * 5 L log2 L (the radix-2 count the
+    survey uses), peak = 148 SMs x 128 lanes x 2 flop x SM clock -- derived, at the clock sampled in this run and
+    at the maximum clock; no measured fp32 peak exists in MEASURED_PEAKS.json."""
+    import math
+    flops = n_seg * 5.0 * nperseg * math.log2(nperseg)
+    tf = flops / (ms * 1e-3) / 1e12
+    mhz_max = float((clocks or {}).get("sm_max_mhz") or 1965.0)
+    mhz_run = float((clocks or {}).get("sm_mhz") or mhz_max)
+    peak_max = 148 * 128 * 2 * mhz_max * 1e6 / 1e12
+    peak_run = 148 * 128 * 2 * mhz_run * 1e6 / 1e12
+    return {"bound": "fp32", "achieved": tf, "unit": "TFLOP/s", "flops": flops, "peak": peak_max, "frac": tf / peak_max,
+            "peak_at_sampled_clock": peak_run, "frac_at_sampled_clock": tf / peak_run,
+            "peak_source": "derived: 148 SMs x 128 fp32 lanes x 2 x clock (max %.0f MHz, sampled %.0f MHz)" % (mhz_max, mhz_run),
+            "note": "5 L log2 L counts a radix-2 FFT; the radix-16/32 kernels execute ~0.53x that many flops, so frac is "
+                    "an upper bound of the ALU time actually spent"}
+
+
+def pair_sharded_cfg4(device, world, rank, steps):
+    """BASELINE config 4 as worded: 64 buoys (2016 pairs), 2^20-sample windows, ONE window whose pairs are sharded
+    over the ranks as blocks of the pair matrix (sharding.tile_pairs: a rank transforms only its blocks' buoys),
+    peak records assembled by one NCCL all-gather (strong scaling).  Timed like the headline: barrier +
+    synchronize on both sides, CUDA events, max over ranks.  Rank 0 also times the same window on its GPU alone
+    (the other ranks wait at a barrier), so the record carries its own 1-GPU reference."""
+    import torch
+    import torch.distributed as dist
+    from radio_mapper_b200 import sharding, synth
+    from radio_mapper_b200.correlator import Correlator
+    B, N = 64, 1 << 20
+    iq, delays = synth.delayed_buoys_torch(4000, B, 1, N, device)       # the same window on every rank (same seed)
+    cor = Correlator(B, N, device=device)
+    P = cor.n_pairs
+    tiles = sharding.tiles_for(B, world)
+
+    def step():
+        rec, _ = cor.run_device_tile(iq, [0], tiles[rank])
+        return sharding.gather_tiled_records(rec, tiles, P, world) if world > 1 else rec
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for _ in range(3):
+        rec = step()
+    torch.cuda.synchronize()
+    want = np.array([delays[0, j] - delays[0, i] for i, j in cor.pairs_host])
+    got = np.empty(P, dtype=np.int64)
+    if world > 1:
+        got[:] = rec[0].cpu().numpy()[:, 0]
+    else:
+        got[tiles[0]["global_index"]] = rec[0].cpu().numpy()[:, 0]
+    ok = bool(np.array_equal(got, want))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = timed(step, steps)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    one_ms = None
+    if rank == 0:
+        for _ in range(2):
+            cor.run_device(iq, [0])
+        torch.cuda.synchronize()
+        one_ms = timed(lambda: cor.run_device(iq, [0]), steps)
+    if world > 1:
+        dist.barrier()
+    out = None
+    if rank == 0:
+        out = {"workload": "cfg4 pair-sharded: 64 buoys (2016 pairs), 2^20-sample window, ONE window, pairs sharded over the ranks",
+               "value": P * N / (ms * 1e-3), "unit": UNIT, "ms_per_window": ms, "n_gpus": world, "scaling": "strong",
+               "steps": steps, "one_gpu_ms_per_window": one_ms, "speedup_vs_one_gpu": one_ms / ms,
+               "buoys_transformed_on_rank0": int(len(tiles[0]["buoys"])), "pairs_on_rank0": int(len(tiles[0]["global_index"])),
+               "passes": cor.plan.pass_lengths, "lags_match_known_delays": ok,
+               "sharding": "blocks of the upper-triangular pair matrix (sharding.tile_pairs); each rank recomputes the "
+                           "forward FFTs of its blocks' buoys from cu8; one NCCL all_gather_into_tensor of the 16-byte "
+                           "peak records per window"}
+    del cor, iq
+    torch.cuda.empty_cache()
+    return out
 
 
 # ----------------------------------------------------------------------------------------
@@ -347,6 +512,16 @@ def run_b200(args, wl):
                         "api": "TDoAProcessor.correlate_stream(ingest source, ...) -> TDoAMeasurements per window",
                         "note": "pinned source: windows are DMA'd in place; file / pipe sources add one host copy into the pinned ring"}
 
+    # ---- BASELINE config 4 as worded: one window, pairs sharded over the ranks (strong scaling) -----------------
+    pair_sharded = None
+    if args.workload == "cfg3":
+        try:
+            pair_sharded = pair_sharded_cfg4(device, world, rank, max(10, args.steps))
+        except Exception as exc:                    # secondary measurement: never fail the headline line
+            pair_sharded = {"error": repr(exc)}
+            if world > 1:
+                raise
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -365,8 +540,7 @@ def run_b200(args, wl):
     traffic, traffic_src = measured_traffic(args.workload, B, P, L)
     per_kernel = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tr = json.load(f)[args.workload]
+        tr = traffic_table()[args.workload]
         unit = 8 * L
         kb = {"contig_inv_pair": unit * (B * tr["pair_pass_read_per_buoy_unit8L"] + P * tr["pair_pass_write_per_pair_unit8L"]),
               "col_inv_argmax": unit * P * tr["argmax_pass_read_per_pair_unit8L"]}
@@ -420,6 +594,7 @@ def run_b200(args, wl):
         welch = {"workload": "2.4 Msps, 64k-bin Welch PSD, 1000 segments", "value": n_seg * nperseg / (wms * 1e-3),
                  "unit": "samples/s", "ms": wms, "passes": wplan.pass_lengths,
                  "hbm_frac": (2.0 * n_seg * nperseg + 4 * nperseg) / (wms * 1e-3) / 1e9 / peak,
+                 "roofline": welch_roofline(n_seg, nperseg, wms, clocks),
                  "kernel": "one thread-block-cluster kernel (8 CTAs hold a 64k segment in distributed shared memory)",
                  "note": "fp32-ALU / DSMEM bound (SURVEY §8d): 2 B/sample of traffic against ~80 flop/sample"}
         del wiq, wplan
@@ -456,17 +631,18 @@ def run_b200(args, wl):
     except Exception as exc:
         detect = {"error": repr(exc)}
 
-    # ---- CPU baseline: the oracle on a bounded sample, this box's host cores ---------------------
-    b = 4 if N <= (1 << 22) else 2
-    sample_iq = iq_host[:b, 0, :].numpy()
-    t_cpu, n_cpu_pairs, cpu_res = cpu_sample_run(sample_iq, 1)
-    cpu_lags = [r[0] for r in cpu_res]
-    import oracle
-    gpu_lags = [int(want[0][k]) for k, (i, j) in enumerate(cor.pairs_host) if i < b and j < b]
-    cpu_baseline = {"value": n_cpu_pairs * N / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-                    "sample": "window 0, first %d buoys (%d pairs): numpy unpack + scipy.signal.correlate + argmax, %.1f s"
-                              % (b, n_cpu_pairs, t_cpu),
-                    "host_cpus": os.cpu_count(), "lags_match_gpu": cpu_lags == gpu_lags}
+    # ---- CPU baseline: the oracle on config 1 exactly, this box's host cores; the same bytes go
+    #      through the GPU path and the lags must agree ---------------------------------------------------------
+    cpu_baseline, cfg1_iq, cfg1_cpu_lags = cpu_baseline_cfg1()
+    try:
+        from radio_mapper_b200 import engine as _eng1
+        p1 = _eng1.Plan(3, 2_048_000, device=device)
+        r1 = _eng1.peaks_to_numpy(p1.xcorr_pairs_peak(p1.forward(torch.from_numpy(cfg1_iq).to(device)),
+                                                       torch.from_numpy(_eng1.pair_table(3)).to(device)))
+        cpu_baseline["lags_match_gpu"] = [int(v) for v in r1["lag"]] == cfg1_cpu_lags
+        del p1
+    except Exception as exc:
+        cpu_baseline["lags_match_gpu"] = repr(exc)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -485,7 +661,7 @@ def run_b200(args, wl):
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "windowed_search": windowed,
-        "welch_psd": welch, "block_detect": detect,
+        "welch_psd": welch, "block_detect": detect, "pair_sharded": pair_sharded,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -163,22 +163,38 @@ class TDoACalculator:
     def measurements_from_lags(self, buoy_ids: Sequence[str], pairs: np.ndarray, lag: np.ndarray,
                                frac: np.ndarray, strength_conf: np.ndarray, sample_rate: float,
                                frequency_mhz: float,
-                               buoy_positions: Optional[Dict[str, BuoyPosition]] = None) -> List[TDoAMeasurement]:
+                               buoy_positions: Optional[Dict[str, BuoyPosition]] = None,
+                               start_ns: Optional[Sequence[int]] = None) -> List[TDoAMeasurement]:
         """Seam between the GPU lag search and :166-170:  dt_ns = round((lag+frac)/fs * 1e9),
-        dd = dt/1e9 * c.  Timing confidence uses the registered buoys when available."""
+        dd = dt/1e9 * c.  Timing confidence uses the registered buoys when available.
+        start_ns: GPS time of each buoy's first sample; when the captures did not start together the arrival-time
+        difference is the lag plus the difference of the capture starts (t_j0 - t_i0), in integer nanoseconds."""
         total = (lag.astype(np.float64) + frac.astype(np.float64)) / float(sample_rate) * 1e9
         dt = np.rint(total).astype(np.int64)
-        out: List[TDoAMeasurement] = []
-        for (i, j), dt_ns, sc in zip(pairs, dt, strength_conf):
-            b1, b2 = buoy_ids[int(i)], buoy_ids[int(j)]
-            conf = float(sc)
-            if buoy_positions:
-                p1, p2 = buoy_positions.get(b1), buoy_positions.get(b2)
-                if p1 and p2:
-                    conf *= self._calculate_timing_confidence(p1, p2)
-            dt_ns = int(dt_ns)
-            out.append(TDoAMeasurement(b1, b2, dt_ns, (dt_ns / 1e9) * self.SPEED_OF_LIGHT, conf, frequency_mhz))
-        return out
+        pr = np.asarray(pairs)
+        if start_ns is not None:
+            t0 = np.asarray(start_ns, dtype=np.int64)
+            dt = dt + (t0[pr[:, 1]] - t0[pr[:, 0]])
+        # same float64 expression per element as :169-170 (dt/1e9 * c), vectorised; the per-pair timing confidence
+        # depends only on the two buoys, so it is evaluated once per pair with the scalar routine of :200-210
+        dd = (dt.astype(np.float64) / 1e9) * self.SPEED_OF_LIGHT
+        conf = strength_conf.astype(np.float64)
+        if buoy_positions:
+            acc = [buoy_positions[b].timing_accuracy_ns if b in buoy_positions else None for b in buoy_ids]
+            cache: Dict[tuple, float] = {}
+            scale = np.ones(len(pr), dtype=np.float64)
+            for k, (i, j) in enumerate(pr.tolist()):
+                a1, a2 = acc[i], acc[j]
+                if a1 is None or a2 is None:
+                    continue
+                v = cache.get((a1, a2))
+                if v is None:
+                    v = cache[(a1, a2)] = min(math.exp(-math.sqrt(a1 ** 2 + a2 ** 2) / 100000), 1.0)
+                scale[k] = v
+            conf = conf * scale
+        names = list(buoy_ids)
+        return [TDoAMeasurement(names[i], names[j], t, d, c, frequency_mhz)
+                for (i, j), t, d, c in zip(pr.tolist(), dt.tolist(), dd.tolist(), conf.tolist())]
 
 
 # ----------------------------------------------------------------------------------------
@@ -407,16 +423,24 @@ class TDoAProcessor:
         """Cross-correlate every buoy pair of every window on the GPU and return one
         `TDoAMeasurement` per (window, pair), window-major, pairs in the i<j order of
         `calculate_tdoa_measurements`.  time_difference_ns = round((lag + frac) / fs * 1e9)."""
-        rec = self.correlate_iq_records(iq_u8, max_lag=max_lag, device=device, distributed=distributed)
-        n_buoys = len(buoy_ids)
+        from .correlator import as_u8_tensor
         from .engine import pair_table
-        pairs = pair_table(n_buoys)
-        if rec.shape[1] != len(pairs):
+        t = as_u8_tensor(iq_u8)
+        if t.ndim == 2:
+            t = t[:, None, :]
+        if t.ndim != 3 or t.shape[2] % 2:
+            raise ValueError("iq_u8 must be uint8[B, W, 2N]")
+        n_buoys = len(buoy_ids)
+        if t.shape[0] != n_buoys:
             raise ValueError("buoy_ids has %d entries but the IQ block has a different buoy count" % n_buoys)
+        pairs = pair_table(n_buoys)
+        cor = self._correlator(t.shape[0], t.shape[2] // 2, device)
         out: List[TDoAMeasurement] = []
-        for w in range(rec.shape[0]):
+        # windows arrive one by one while the GPU works on the ones behind them: the per-window object building
+        # below overlaps the kernels
+        for rec in cor.run_iter(t, max_lag=max_lag, distributed=distributed):
             out.extend(self.tdoa_calculator.measurements_from_lags(
-                buoy_ids, pairs, rec["lag"][w], rec["frac"][w], rec["coherence"][w], sample_rate, frequency_mhz,
+                buoy_ids, pairs, rec["lag"], rec["frac"], rec["coherence"], sample_rate, frequency_mhz,
                 self.buoy_positions))
         return out
 
@@ -442,6 +466,23 @@ class TDoAProcessor:
             yield self.tdoa_calculator.measurements_from_lags(
                 buoy_ids, pairs, rec["lag"], rec["frac"], rec["coherence"], sample_rate, frequency_mhz,
                 self.buoy_positions)
+
+    def correlate_window_frames(self, frames, buoy_ids: Sequence[str], samples_per_window: int,
+                                max_lag: Optional[int] = None, device=None, depth: int = 4):
+        """Central-side consumer of the binary `cu8_window` frames (wire.py; SURVEY §8f-1: raw IQ windows next to the
+        reference's JSON `signal_detection` frames, central_processor.py:305-335).  `frames` is an iterable of binary
+        frames (or wire.Cu8Window objects) from the buoys in any interleaving; every time all `buoy_ids` have
+        delivered a window it is correlated on the GPU and (window_index, List[TDoAMeasurement]) is yielded, with
+        time_difference_ns = lag/fs plus the difference of the buoys' capture-start GPS timestamps."""
+        from . import wire
+        from .engine import pair_table
+        asm = wire.WindowAssembler(buoy_ids, samples_per_window, depth=depth)
+        pairs = pair_table(len(buoy_ids))
+        for w, block, stamps, fs, fc in asm.feed(frames):
+            rec = self.correlate_iq_records(block, max_lag=max_lag, device=device)
+            yield w, self.tdoa_calculator.measurements_from_lags(
+                list(buoy_ids), pairs, rec["lag"][0], rec["frac"][0], rec["coherence"][0], fs, fc / 1e6,
+                self.buoy_positions, start_ns=stamps)
 
     def triangulate_iq(self, iq_u8, buoy_ids: Sequence[str], sample_rate: float = 2048000,
                        frequency_mhz: float = 0.0, signal_type: str = "unknown",

@@ -383,10 +383,14 @@ def test_iq_stream_client_module_matches_reference_golden(golden_dir):
     assert np.array_equal(block.view(np.uint32), xs.view(np.uint32))
     det = sc.SignalDetector("NODE_T")
     got = det.detect_signals(block, float(g["center_hz"]))
-    assert all(isinstance(d, sc.SignalDetection) and d.node_id == "NODE_T" and d.detection_method == "fft_peak"
-               and len(d.iq_samples) == 256 for d in got)
     bins, _ = det.detect_signals_indexed(block, float(g["center_hz"]))
     assert len(bins) == len(got)
+    n = len(block)
+    for k, d in zip(bins, got):
+        assert isinstance(d, sc.SignalDetection) and d.node_id == "NODE_T" and d.detection_method == "fft_peak"
+        start = max(0, k - 128)                                     # _extract_signal_samples (:306-316)
+        assert len(d.iq_samples) == min(n, start + 256) - start
+        assert d.iq_samples[0] == complex(block[start])
     _check_stream_detections(dict(zip(bins, got)), want_by_bin, p)
     assert det.detect_signals(np.zeros(0, np.complex64), 100e6) == []  # errors are logged and yield [] (:249-252)
 

@@ -115,3 +115,30 @@ def test_streamed_records_equal_batched(tmp_path, depth):
     again = [m for meas in proc.correlate_stream(ingest.ArraySource(iq.reshape(B, -1), n), ids, 2_048_000, 433.9,
                                                  depth=depth, max_windows=3) for m in meas]
     assert again == batched[:18]
+
+
+@pytest.mark.gpu
+def test_cu8_window_frames_reach_the_correlator():
+    """binary cu8_window frames from the buoys (any interleaving) -> WindowAssembler -> GPU correlate.
+    Measurements equal correlate_iq on the same bytes; capture-start offsets enter time_difference_ns exactly."""
+    import random
+    from radio_mapper_b200 import wire
+    from radio_mapper_b200.tdoa_processor import TDOAProcessor
+    n, fs, B, W = 1 << 15, 2048000, 4, 3
+    ids = ["B%d" % b for b in range(B)]
+    blocks = [synth.delayed_buoys(40 + w, B, n)[0] for w in range(W)]          # uint8[B, 2N] per window
+    base = 1_735_689_600_000_000_000
+    start = {(b, w): base + w * int(n / fs * 1e9) + (137 * b if w == 1 else 0) for b in range(B) for w in range(W)}
+    frames = [wire.pack_cu8_window(ids[b], w, start[(b, w)], fs, 121.5e6, blocks[w][b]) for w in range(W) for b in range(B)]
+    random.Random(3).shuffle(frames)
+    proc = TDOAProcessor()
+    got = dict(proc.correlate_window_frames(frames, ids, n, depth=4))
+    assert sorted(got) == [0, 1, 2]
+    for w in range(W):
+        direct = proc.correlate_iq(blocks[w][:, None, :], ids, fs, 121.5)
+        assert len(got[w]) == len(direct) == 6
+        for g, d in zip(got[w], direct):
+            i, j = ids.index(g.buoy1_id), ids.index(g.buoy2_id)
+            assert (g.buoy1_id, g.buoy2_id, g.frequency_mhz) == (d.buoy1_id, d.buoy2_id, 121.5)
+            assert g.time_difference_ns == d.time_difference_ns + (start[(j, w)] - start[(i, w)])
+            assert g.confidence == d.confidence
