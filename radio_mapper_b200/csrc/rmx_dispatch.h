@@ -23,6 +23,9 @@ struct TmaKernelEntry {
 // persistent TMA-fed arg-max pass (32 values per thread; n = 512 or 1024)
 TmaKernelEntry get_argmax_tma_kernel(int logn, int loge, bool pre_twiddled);
 
+// persistent TMA-fed forward pass 0 from cu8 (n = 512, 1024 with 32 values per thread; n = 128, 256 with 16)
+TmaKernelEntry get_fwd_tma_kernel(int logn, int loge);
+
 // X_i-stationary pair pass (one row per tile, 16 values per thread: n = 4096); run = pairs per CTA
 struct PairRunEntry {
     PassKernel fn;       // nullptr if not instantiated

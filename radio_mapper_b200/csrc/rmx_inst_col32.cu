@@ -38,6 +38,22 @@ static TmaKernelEntry tma_entry() {
                           GEO::N < 256 ? GEO::N : 256, argmax_tma_ctas(5)};
 }
 
+template <int LOGN, int LOGE>
+static TmaKernelEntry fwd_tma_entry() {
+    using GEO = TileGeom<LOGN, LOGE, true>;
+    const size_t stage = size_t(GEO::N) * 2 * GEO::G;
+    return TmaKernelEntry{(ArgmaxTmaKernel)k_col_fwd_cu8_tma<LOGN, LOGE>, ((GEO::SMEM_BYTES + 127) & ~size_t(127)) + 128 + 2 * stage,
+                          GEO::LOGG, GEO::N < 256 ? GEO::N : 256, min_ctas(LOGE)};
+}
+
+TmaKernelEntry get_fwd_tma_kernel(int logn, int loge) {
+    if (loge == 5 && logn == 10) return fwd_tma_entry<10, 5>();
+    if (loge == 5 && logn == 9) return fwd_tma_entry<9, 5>();
+    if (loge == 4 && logn == 8) return fwd_tma_entry<8, 4>();
+    if (loge == 4 && logn == 7) return fwd_tma_entry<7, 4>();
+    return TmaKernelEntry{nullptr, 0, 0, 0, 0};
+}
+
 TmaKernelEntry get_argmax_tma_kernel16(int logn, bool pre);   // rmx_inst_col.cu
 
 TmaKernelEntry get_argmax_tma_kernel(int logn, int loge, bool pre) {

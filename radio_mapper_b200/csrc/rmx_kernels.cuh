@@ -558,10 +558,108 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, int c0, int c1, int c2, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
 // global -> shared bulk copy (TMA engine, 1-D): `bytes` a multiple of 16, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_load_1d(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// forward pass 0 from cu8, persistent and TMA-fed (north_star stage 2: "window tiles staged into SMEM by TMA")
+// ---------------------------------------------------------------------------------------
+// Same arithmetic as k_col<..., K_FWD_CU8>: column FFTs of length n at stride s over the raw cu8 samples of each
+// signal, then the inter-pass twiddle.  The n x 2G-byte tile of raw bytes (n rows of the [row][2s bytes] view of
+// the window, G adjacent columns) is brought in by 3-D TMA box loads {2G bytes, <=256 rows, 1 signal} completing
+// on an mbarrier, double-buffered: the load of tile t+1 is issued before tile t is unpacked, so no thread ever
+// waits on a global load of raw samples and no registers stage them.  Rows past the valid samples (zero padding)
+// are outside the tensor map and arrive as zero bytes; the unpack still masks them (a zero BYTE is -127.5).
+// tmap: UINT8 tensor {2s, n_valid_rows, n_items}, strides {2s, cu8_stride} bytes, box {2G, min(n,256), 1}.
+template <int LOGN, int LOGE>
+__global__ void __launch_bounds__(kThreads, min_ctas(LOGE)) k_col_fwd_cu8_tma(const PassParams p, const __grid_constant__ CUtensorMap tmap,
+                                                                             const unsigned n_tiles) {
+    using GEO = TileGeom<LOGN, LOGE, true>;
+    constexpr int E = GEO::E, NT = GEO::NT, G = GEO::G, LOGG = GEO::LOGG, N = GEO::N;
+    constexpr int BOX_ROWS = N < 256 ? N : 256;
+    constexpr uint32_t STAGE_BYTES = (uint32_t)N * 2u * G;
+    extern __shared__ float2 smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    // [exchange area | stage 0 | stage 1], stages 128-byte aligned
+    float2* smem = smem_raw;
+    unsigned char* stage0 = reinterpret_cast<unsigned char*>(smem_raw) + ((GEO::SMEM_BYTES + 127) & ~size_t(127));
+    stage0 += (128u - (smem_u32(stage0) & 127u)) & 127u;
+
+    int g, i0;
+    GEO::thread_map(threadIdx.x, g, i0);
+    const int logS = p.logS;
+    const int logM = LOGN + logS;
+    const int log_tpb = logS - LOGG;                       // tiles per block (log2)
+    const int log_bpi = p.logL - logM;                     // blocks per item (log2); 0 for pass 0 of a plan
+
+    auto issue = [&](unsigned idx, int buf) {              // one thread
+        const unsigned jt = idx & ((1u << log_tpb) - 1u);
+        const unsigned item = idx >> (log_tpb + log_bpi);
+        mbar_expect_tx(&mbar[buf], STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < N / BOX_ROWS; ++c)
+            tma_load_3d(stage0 + buf * STAGE_BYTES + c * BOX_ROWS * 2 * G, &tmap, (int)(jt << (LOGG + 1)), c * BOX_ROWS, (int)item, &mbar[buf]);
+    };
+
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned idx = blockIdx.x;
+    if (threadIdx.x == 0 && idx < n_tiles) issue(idx, 0);
+    uint32_t parity[2] = {0u, 0u};
+    int buf = 0;
+
+    for (; idx < n_tiles; idx += gridDim.x, buf ^= 1) {
+        const unsigned next = idx + gridDim.x;
+        // the other stage was last read two iterations ago, before that iteration's __syncthreads
+        if (threadIdx.x == 0 && next < n_tiles) {
+            fence_proxy_async();
+            issue(next, buf ^ 1);
+        }
+        const unsigned jt = idx & ((1u << log_tpb) - 1u);
+        const long long item = idx >> (log_tpb + log_bpi);
+        const unsigned j = (jt << LOGG) + g;               // column within the block
+        const long long base = j;                          // pass 0: one block per item
+
+        mbar_wait(&mbar[buf], parity[buf]);
+        parity[buf] ^= 1u;
+        const uchar2* sb2 = reinterpret_cast<const uchar2*>(stage0 + buf * STAGE_BYTES);
+        float2 r[E];
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+            const int row = i0 + u * NT;
+            const long long sidx = base + ((long long)row << logS);
+            const uchar2 b = sb2[row * G + g];
+            float2 v = make_float2(0.f, 0.f);
+            if (sidx < p.n_samples) v = make_float2((float)b.x - 127.5f, (float)b.y - 127.5f);
+            r[u] = v;
+        }
+        __syncthreads();                                   // stage consumed (it is refilled one iteration later); exchange area free
+
+        fft_tile<GEO, false, (RMX_PAIR_TWTREE != 0)>(r, smem, g, i0, p.tabs);
+        {
+            float2 tw[E];
+            row_twiddles<E>(tw, j, (uint32_t)i0, (uint32_t)NT, logM, false, 1.0f);
+#pragma unroll
+            for (int u = 0; u < E; ++u) r[u] = cmul(r[u], tw[u]);
+        }
+        float2* __restrict__ out = p.dst + item * p.src_item_stride + base + ((long long)i0 << logS);
+        const long long rstride = (long long)NT << logS;
+#pragma unroll
+        for (int u = 0; u < E; ++u) { *out = r[u]; out += rstride; }
+        if constexpr (GEO::NSTAGES > 1) __syncthreads();   // exchange area is reused by the next tile
+    }
 }
 
 // ---------------------------------------------------------------------------------------

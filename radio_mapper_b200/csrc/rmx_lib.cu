@@ -80,6 +80,7 @@ struct rmx_plan {
     int pair_prefetch = 1;            // next X_j row by bulk copy into shared memory
     long long fwd_group_bytes = 0;    // forward passes run over groups of signals whose spectra fit this many bytes (0 = all at once)
     int welch_clusters = 0;           // resident clusters of the Welch kernel (0 = occupancy query)
+    int fwd_tma = 0;                  // forward pass 0 through the persistent TMA-fed kernel
 };
 
 static int build_stage_tables(rmx_plan* pl, int logn, int loge, StageTables* out) {
@@ -274,6 +275,7 @@ extern "C" int rmx_plan_set_option(rmx_plan* pl, const char* name, long long val
     else if (!strcmp(name, "pair_prefetch")) pl->pair_prefetch = value != 0;
     else if (!strcmp(name, "fwd_group_bytes")) pl->fwd_group_bytes = value < 0 ? 0 : value;
     else if (!strcmp(name, "welch_clusters")) pl->welch_clusters = (int)std::max<long long>(0, value);
+    else if (!strcmp(name, "fwd_tma")) pl->fwd_tma = value != 0;
     else return fail(RMX_ERR_ARG, "unknown plan option '%s'", name);
     return RMX_OK;
 }
@@ -451,6 +453,40 @@ static int launch_argmax_tma(const rmx_plan* pl, const PassParams& pp, bool pre,
     return RMX_OK;
 }
 
+// forward pass 0 from cu8 through the persistent TMA-fed kernel; *taken = false when this plan / input cannot take it
+static int launch_fwd_tma(const rmx_plan* pl, const PassParams& pp, int cnt, cudaStream_t st, bool* taken) {
+    *taken = false;
+    if (!pl->fwd_tma || pp.window != nullptr || pl->n_passes < 2) return RMX_OK;
+    const TmaKernelEntry k = get_fwd_tma_kernel(pl->logn[0], pl->loge[0]);
+    auto enc = tensor_map_encoder();
+    if (!k.fn || !enc) return RMX_OK;
+    if (pl->logn[0] + pl->logs[0] != pl->logL) return RMX_OK;            // pass 0 spans the whole item
+    const unsigned long long s = 1ULL << pl->logs[0];
+    if ((unsigned long long)pl->n_samples % s != 0) return RMX_OK;       // whole rows only (no read past the last signal)
+    const unsigned long long rows = (unsigned long long)pl->n_samples >> pl->logs[0];
+    if (rows == 0 || ((reinterpret_cast<uintptr_t>(pp.cu8) | (uintptr_t)pp.cu8_stride) & 15) != 0) return RMX_OK;
+    if (2 * s > (1ULL << 32) - 1) return RMX_OK;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {2 * s, rows, (cuuint64_t)cnt};
+    const cuuint64_t gstride[2] = {2 * s, (cuuint64_t)pp.cu8_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)(2u << k.logG), (cuuint32_t)k.box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(pp.cu8), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RMX_ERR_CUDA, "cuTensorMapEncodeTiled (forward) failed (%d)", (int)r);
+    const unsigned n_tiles = tiles_of(pl, 0, cnt);
+    const unsigned grid = std::min<unsigned>(n_tiles, (unsigned)k.ctas_per_sm * (unsigned)sm_count());
+    CUDA_TRY(cudaFuncSetAttribute((const void*)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem_bytes));
+    {
+        ProfScope prof(pl, "col_fwd_cu8", st);
+        k.fn<<<grid, kThreads, k.smem_bytes, st>>>(pp, tmap, n_tiles);
+    }
+    LAUNCH_CHECK("col_fwd_cu8_tma");
+    *taken = true;
+    return RMX_OK;
+}
+
 // innermost inverse pass over `cnt` pairs
 static int launch_pair_pass(const rmx_plan* pl, const PassParams& pp, int cnt, cudaStream_t st) {
     const int last = pl->n_passes - 1;
@@ -499,6 +535,12 @@ static int forward_cu8(const rmx_plan* pl, const uint8_t* iq, long long stride_b
         for (int t = 0; t < np - 1; ++t) {
             pp.tabs = pl->tabs[t];
             pp.logS = pl->logs[t];
+            if (t == 0) {
+                bool taken = false;
+                int rc = launch_fwd_tma(pl, pp, cnt, st, &taken);
+                if (rc) return rc;
+                if (taken) continue;
+            }
             int rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], t == 0 ? K_FWD_CU8 : K_FWD),
                                  t == 0 ? "col_fwd_cu8" : "col_fwd", dim3(tiles_of(pl, t, cnt)), pp, st);
             if (rc) return rc;
