@@ -476,6 +476,22 @@ def run_b200(args, wl):
         e2e_s = float(t.item())
     assert len(meas) == W * P
     e2e_value = P * N * W * world * args.steps / e2e_s
+    # the bus under the e2e number: pinned host -> device bandwidth of this box, and the copy time of one step
+    # (only the first window's copy cannot hide behind kernels within a correlate_iq call)
+    h2d_gbs = None
+    try:
+        scratch = torch.empty_like(iq_dev)
+        hb0, hb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        scratch.copy_(iq_host, non_blocking=True)
+        torch.cuda.synchronize()
+        hb0.record()
+        scratch.copy_(iq_host, non_blocking=True)
+        hb1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = iq_host.numel() / (hb0.elapsed_time(hb1) * 1e-3) / 1e9
+        del scratch
+    except Exception:
+        h2d_gbs = None
 
     # ---- the same windows through the streaming API (ingest.ArraySource -> pinned ring -> copy stream ->
     #      correlator): the copy of window w+1 overlaps the kernels of window w across step boundaries too ----
@@ -655,6 +671,9 @@ def run_b200(args, wl):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(iq_host.numel()),
                 "d2h_bytes_per_step": int(W * P * 16 + W * B * 8), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "h2d_gbs_measured": h2d_gbs,
+                "h2d_ms_per_step": (iq_host.numel() / (h2d_gbs * 1e9) * 1e3) if h2d_gbs else None,
+                "h2d_ms_first_window": (iq_host.numel() / W / (h2d_gbs * 1e9) * 1e3) if h2d_gbs else None,
                 "streaming": stream_value,
                 "api": "TDoAProcessor.correlate_iq(pinned host uint8[B,W,2N]) -> List[TDoAMeasurement]"},
         "gpu_launches": launches,

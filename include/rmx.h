@@ -84,8 +84,9 @@ RMX_API int rmx_plan_create(rmx_plan** plan, int n_signals, size_t n_samples, si
  * X_i-stationary row pass; "pair_prefetch" = 0 | 1 next X_j row by bulk copy into shared memory;
  * "fwd_group_bytes" = forward passes run over groups of signals whose spectra fit this many bytes, so a pass
  * reads the previous one's output from L2 (0 = all signals per launch); "welch_clusters" = resident clusters of
- * the Welch kernel (0 = occupancy query); "fwd_tma" = 0 | 1 forward pass 0 through the persistent kernel that stages
- * the raw cu8 tiles in shared memory by 3-D TMA box loads (whole-row windows, 16-byte aligned input). */
+ * the Welch kernel (0 = occupancy query); "fwd_tma" = 1 | 0 forward pass 0 through the persistent kernel that stages
+ * the raw cu8 tiles in shared memory by 3-D TMA box loads (default; taken for whole-row windows and 16-byte aligned
+ * input, otherwise -- and with 0 -- the per-thread 128-bit staging kernel runs). */
 RMX_API int rmx_plan_set_option(rmx_plan* plan, const char* name, long long value);
 RMX_API int rmx_plan_destroy(rmx_plan* plan);
 /* number of passes and their lengths n_t (outermost first); returns n_passes */

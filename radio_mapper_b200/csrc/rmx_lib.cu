@@ -80,7 +80,7 @@ struct rmx_plan {
     int pair_prefetch = 1;            // next X_j row by bulk copy into shared memory
     long long fwd_group_bytes = 0;    // forward passes run over groups of signals whose spectra fit this many bytes (0 = all at once)
     int welch_clusters = 0;           // resident clusters of the Welch kernel (0 = occupancy query)
-    int fwd_tma = 0;                  // forward pass 0 through the persistent TMA-fed kernel
+    int fwd_tma = 1;                  // forward pass 0 through the persistent TMA-fed kernel (measured -10..-15 % on that pass)
 };
 
 static int build_stage_tables(rmx_plan* pl, int logn, int loge, StageTables* out) {

@@ -16,6 +16,13 @@ for n_windows in (5, 1):
     proc = TDOAProcessor()
     rec = proc.correlate_iq_records(torch.from_numpy(iq).pin_memory(), distributed=True)
     ok = all(np.array_equal(rec["lag"][w], oracle.xcorr_pairs_peak(blocks[w])["lag"]) for w in range(n_windows))
-    print(f"rank {rank} windows={n_windows} shape={rec.shape} lags_ok={ok} coherence_min={rec['coherence'].min():.3f}", flush=True)
-    assert ok
+    # the distributed result must be BYTE-identical to the single-GPU one (windows dealt to ranks when there are
+    # at least as many windows as ranks, blocks of the pair matrix otherwise): same kernels on the same spectra
+    single = TDOAProcessor().correlate_iq_records(torch.from_numpy(iq).pin_memory(), distributed=False)
+    same = all(np.array_equal(rec[f], single[f]) for f in ("lag", "peak", "frac", "coherence"))
+    dev = TDOAProcessor().correlate_iq_records(torch.from_numpy(iq).cuda(), distributed=True)     # device-resident input
+    same_dev = all(np.array_equal(dev[f], single[f]) for f in ("lag", "peak", "frac", "coherence"))
+    print(f"rank {rank} windows={n_windows} shape={rec.shape} lags_ok={ok} identical_to_single_gpu={same} device_input_identical={same_dev} "
+          f"coherence_min={rec['coherence'].min():.3f}", flush=True)
+    assert ok and same and same_dev
 dist.destroy_process_group()
