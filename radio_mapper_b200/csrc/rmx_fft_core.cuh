@@ -347,12 +347,19 @@ __device__ __forceinline__ void row_twiddles(float2 (&tw)[E], uint32_t j, uint32
 // shared by the whole CTA (one row per tile): they are read from shared memory, each an exactly
 // reduced root, so a thread evaluates one sincospif instead of 1 + log2(E)/2.
 template <int E>
-__device__ __forceinline__ void row_twiddles_shared(float2 (&tw)[E], uint32_t j, uint32_t i0, int logm, bool inverse,
-                                                    float scale, const float2* pw_shared) {
+__device__ __forceinline__ float2 row_twiddle_base(uint32_t j, uint32_t i0, int logm, bool inverse, float scale) {
+    // tw[0] of row_twiddles_shared: depends on the row and the thread only, so a CTA that walks several pairs of
+    // one row evaluates it once
     const uint32_t mask = (logm >= 32) ? 0xffffffffu : ((1u << logm) - 1u);
-    tw[0] = unit_root((j * i0) & mask, logm, inverse);
-    tw[0].x *= scale;
-    tw[0].y *= scale;
+    float2 t = unit_root((j * i0) & mask, logm, inverse);
+    t.x *= scale;
+    t.y *= scale;
+    return t;
+}
+
+template <int E>
+__device__ __forceinline__ void row_twiddles_from_base(float2 (&tw)[E], float2 base, const float2* pw_shared) {
+    tw[0] = base;
     static_for<0, ilog2(E)>([&](auto Z_) {
         constexpr int z = decltype(Z_)::value;
         const float2 pw = pw_shared[z];
@@ -361,6 +368,12 @@ __device__ __forceinline__ void row_twiddles_shared(float2 (&tw)[E], uint32_t j,
             tw[u + (1 << z)] = cmul(tw[u], pw);
         });
     });
+}
+
+template <int E>
+__device__ __forceinline__ void row_twiddles_shared(float2 (&tw)[E], uint32_t j, uint32_t i0, int logm, bool inverse,
+                                                    float scale, const float2* pw_shared) {
+    row_twiddles_from_base<E>(tw, row_twiddle_base<E>(j, i0, logm, inverse, scale), pw_shared);
 }
 
 }  // namespace rmx

@@ -26,9 +26,10 @@ KernelEntry get_contig_kernel32(int logn, int mode) {
 WelchClusterEntry get_welch_cluster_kernel(int logc) {
     using GEO = TileGeom<13, 5, false>;
     switch (logc) {
-        case 1: return WelchClusterEntry{(WelchClusterKernel)k_welch_cluster<1>, GEO::SMEM_BYTES, 2};
-        case 2: return WelchClusterEntry{(WelchClusterKernel)k_welch_cluster<2>, GEO::SMEM_BYTES, 4};
-        case 3: return WelchClusterEntry{(WelchClusterKernel)k_welch_cluster<3>, GEO::SMEM_BYTES, 8};
+        // + the CTA's window slice: E values per thread
+        case 1: return WelchClusterEntry{(WelchClusterKernel)k_welch_cluster<1>, GEO::SMEM_BYTES + GEO::TILE * sizeof(float), 2};
+        case 2: return WelchClusterEntry{(WelchClusterKernel)k_welch_cluster<2>, GEO::SMEM_BYTES + GEO::TILE * sizeof(float), 4};
+        case 3: return WelchClusterEntry{(WelchClusterKernel)k_welch_cluster<3>, GEO::SMEM_BYTES + GEO::TILE * sizeof(float), 8};
         default: return WelchClusterEntry{nullptr, 0, 0};
     }
 }

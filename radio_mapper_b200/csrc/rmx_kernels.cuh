@@ -699,6 +699,8 @@ __global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run
     const int first = (int)blk * RUN;
     const int last = min(first + RUN, p.n_items);
     uint32_t parity = 0;
+    // w_M^{row*i0} (times the scale): the same for every pair of the run -- one sincospif per CTA walk, not per pair
+    const float2 tw_base = p.post_logm > 0 ? row_twiddle_base<E>(rr, (uint32_t)i0, p.post_logm, true, p.post_scale) : make_float2(1.f, 0.f);
     if constexpr (PREFETCH) {
         if (threadIdx.x == 0) {
             mbar_init(&mbar, 1);
@@ -742,7 +744,7 @@ __global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run
         fft_tile<GEO, true, (RMX_PAIR_TWTREE != 0)>(r, smem, g, i0, p.tabs);
         if (p.post_logm > 0) {
             float2 tw[E];
-            row_twiddles_shared<E>(tw, rr, (uint32_t)i0, p.post_logm, true, p.post_scale, s_pw);
+            row_twiddles_from_base<E>(tw, tw_base, s_pw);
 #pragma unroll
             for (int u = 0; u < E; ++u) r[u] = cmul(r[u], tw[u]);
         }
@@ -782,6 +784,8 @@ __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile
 __device__ __forceinline__ unsigned cluster_id_x() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cluster_count_x() { unsigned r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// arrive without release semantics: orders nothing but the barrier itself (no MEMBAR); for "I am done READING" hand-offs
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void st_cluster_f2(uint32_t local_addr, unsigned rank, float2 v) {
     uint32_t remote;
@@ -804,10 +808,21 @@ __global__ void __launch_bounds__(kThreads, 2) k_welch_cluster(const WelchCluste
     constexpr int E = GEO::E, NT = GEO::NT, N = GEO::N, C = 1 << LOGC;
     constexpr int CPT = E / C;                               // columns per thread in the column phase
     extern __shared__ float2 smem[];
+    // window values this CTA needs (its N/C columns of all C rows), behind the row / exchange buffer: they are the
+    // same for every segment, so they are read from global memory once instead of once per segment
+    float* s_win = reinterpret_cast<float*>(smem + GEO::NP);
     const unsigned c = cluster_ctarank();
     const int t = threadIdx.x, i0 = threadIdx.x, g = 0;
     const uint32_t lmask = (1u << p.logL) - 1u;
     const uint32_t smem_base = smem_u32(smem);
+#pragma unroll
+    for (int v = 0; v < CPT; ++v)
+#pragma unroll
+        for (int r = 0; r < C; ++r)
+            s_win[(v * C + r) * kThreads + t] = __ldg(p.window + (uint32_t)r * N + c * (uint32_t)(N / C) + (uint32_t)t + 256u * v);
+    // every CTA of the cluster has started before anyone stores into a peer's shared memory
+    cluster_arrive_relaxed();
+    cluster_wait();
 
     float acc[E];
 #pragma unroll
@@ -827,7 +842,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_welch_cluster(const WelchCluste
             for (int r = 0; r < C; ++r) {
                 const uint32_t n = (uint32_t)r * N + j;
                 const uchar2 b = *reinterpret_cast<const uchar2*>(in + 2 * (size_t)n);
-                const float w = __ldg(p.window + n);
+                const float w = s_win[(v * C + r) * kThreads + t];
                 y[v][r] = make_float2(((float)b.x - 127.5f) * w, ((float)b.y - 127.5f) * w);
             }
             dft_regs<C, false>(y[v]);
@@ -861,7 +876,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_welch_cluster(const WelchCluste
         fft_tile<GEO, false>(r, smem, g, i0, p.tabs);
 #pragma unroll
         for (int u = 0; u < E; ++u) acc[u] += cnorm2(r[u]);
-        cluster_arrive();                                    // my reads of the buffer are done (matched at the top)
+        // my READS of the buffer are done (matched at the top): nothing this CTA wrote has to become visible to
+        // the others here, so the arrive carries no release fence (saves a MEMBAR.ALL.GPU + ERRBAR per segment)
+        cluster_arrive_relaxed();
     }
     if (!first) cluster_wait();
     float* __restrict__ out = p.accum + (size_t)c * N;
