@@ -95,6 +95,7 @@ struct PassParams {
     int post_logm;            // C_INV_PAIR: log2(M) of the next column pass (0 = do not twiddle)
     int post_logn;            // C_INV_PAIR: log2 of that pass's transform length (row index = row mod n)
     float post_scale;         // C_INV_PAIR: scale folded into those twiddles (a power of two)
+    int prefetch;             // C_FWD_PSD: next segment's row by bulk copy into a landing buffer behind the exchange area
 };
 
 enum ContigMode { C_FWD = 0, C_FWD_CU8 = 1, C_INV_PAIR = 2, C_FWD_PSD = 3, C_INV_PAIR_WIN2 = 4, C_INV_PAIR_WIN4 = 5, C_INV_PAIR_WIN8 = 6 };
@@ -126,6 +127,43 @@ __device__ __forceinline__ void bulk_store_1d(void* gdst, const void* ssrc, uint
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------
+// TMA helpers (sm_100a): 2-D tiled bulk-tensor loads completing on an mbarrier
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, int c0, int c1, int c2, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+// global -> shared bulk copy (TMA engine, 1-D): `bytes` a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_load_1d(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 
 __device__ __forceinline__ float2 load_cu8_sample(const uint8_t* base, long long idx) {
     // (float)u8 - 127.5f, I then Q: exactly the reference's unpack (buoy_node.py:392-398)
@@ -262,6 +300,46 @@ k_contig(const PassParams p) {
         const long long row = (long long)blockIdx.x * G + g;          // row within a signal
         const int first = blockIdx.y * p.items_per_cta;
         const int last = min(first + p.items_per_cta, p.n_items);
+        if constexpr (G == 1 && GEO::NSTAGES > 1) {
+            if (p.prefetch) {
+                // the row of the NEXT segment arrives by one bulk copy (TMA engine, mbarrier-completed) while this
+                // one is transformed: the pass streams the spectra workspace from HBM, so every iteration would
+                // otherwise start with a full-latency load
+                __shared__ __align__(8) unsigned long long mbar;
+                constexpr uint32_t ROW_BYTES = (uint32_t)(GEO::N * sizeof(float2));
+                float2* land = smem + ((GEO::NP + 15) & ~15);
+                const float2* __restrict__ base = p.src + (row << LOGN);
+                if (threadIdx.x == 0) {
+                    mbar_init(&mbar, 1);
+                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                    if (first < last) {
+                        mbar_expect_tx(&mbar, ROW_BYTES);
+                        bulk_load_1d(land, base + (long long)first * p.src_item_stride, ROW_BYTES, &mbar);
+                    }
+                }
+                __syncthreads();
+                uint32_t parity = 0;
+                for (int it = first; it < last; ++it) {
+                    mbar_wait(&mbar, parity);
+                    parity ^= 1u;
+#pragma unroll
+                    for (int u = 0; u < E; ++u) r[u] = land[i0 + u * NT];
+                    __syncthreads();      // landing buffer consumed; everyone is past the previous exchange reads
+                    if (threadIdx.x == 0 && it + 1 < last) {
+                        fence_proxy_async();
+                        mbar_expect_tx(&mbar, ROW_BYTES);
+                        bulk_load_1d(land, base + (long long)(it + 1) * p.src_item_stride, ROW_BYTES, &mbar);
+                    }
+                    fft_tile<GEO, false>(r, smem, g, i0, p.tabs);
+#pragma unroll
+                    for (int u = 0; u < E; ++u) acc[u] += cnorm2(r[u]);
+                }
+                float* __restrict__ outp = p.accum + (row << LOGN);
+#pragma unroll
+                for (int u = 0; u < E; ++u) atomicAdd(outp + i0 + u * NT, acc[u]);
+                return;
+            }
+        }
         for (int it = first; it < last; ++it) {
             const float2* __restrict__ in = p.src + (long long)it * p.src_item_stride + (row << LOGN);
 #pragma unroll
@@ -534,42 +612,6 @@ __global__ void __launch_bounds__(kThreads, (MODE == K_INV_ARGMAX_PRE && LOGE ==
 }
 
 // ---------------------------------------------------------------------------------------
-// TMA helpers (sm_100a): 2-D tiled bulk-tensor loads completing on an mbarrier
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, unsigned long long* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, int c0, int c1, int c2, unsigned long long* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
-}
-// global -> shared bulk copy (TMA engine, 1-D): `bytes` a multiple of 16, both addresses 16-byte aligned
-__device__ __forceinline__ void bulk_load_1d(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// ---------------------------------------------------------------------------------------
 // forward pass 0 from cu8, persistent and TMA-fed (north_star stage 2: "window tiles staged into SMEM by TMA")
 // ---------------------------------------------------------------------------------------
 // Same arithmetic as k_col<..., K_FWD_CU8>: column FFTs of length n at stride s over the raw cu8 samples of each
@@ -578,7 +620,8 @@ __device__ __forceinline__ void bulk_load_1d(void* sdst, const void* gsrc, uint3
 // on an mbarrier, double-buffered: the load of tile t+1 is issued before tile t is unpacked, so no thread ever
 // waits on a global load of raw samples and no registers stage them.  Rows past the valid samples (zero padding)
 // are outside the tensor map and arrive as zero bytes; the unpack still masks them (a zero BYTE is -127.5).
-// tmap: UINT8 tensor {2s, n_valid_rows, n_items}, strides {2s, cu8_stride} bytes, box {2G, min(n,256), 1}.
+// tmap: UINT16 tensor (one element = one I,Q byte pair) {s, n_valid_rows, n_items}, strides {2s, cu8_stride} bytes,
+// box {G, min(n,256), 1}.
 template <int LOGN, int LOGE>
 __global__ void __launch_bounds__(kThreads, min_ctas(LOGE)) k_col_fwd_cu8_tma(const PassParams p, const __grid_constant__ CUtensorMap tmap,
                                                                              const unsigned n_tiles) {
@@ -606,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(LOGE)) k_col_fwd_cu8_tma(co
         mbar_expect_tx(&mbar[buf], STAGE_BYTES);
 #pragma unroll
         for (int c = 0; c < N / BOX_ROWS; ++c)
-            tma_load_3d(stage0 + buf * STAGE_BYTES + c * BOX_ROWS * 2 * G, &tmap, (int)(jt << (LOGG + 1)), c * BOX_ROWS, (int)item, &mbar[buf]);
+            tma_load_3d(stage0 + buf * STAGE_BYTES + c * BOX_ROWS * 2 * G, &tmap, (int)(jt << LOGG), c * BOX_ROWS, (int)item, &mbar[buf]);
     };
 
     if (threadIdx.x == 0) {
@@ -642,7 +685,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(LOGE)) k_col_fwd_cu8_tma(co
             const long long sidx = base + ((long long)row << logS);
             const uchar2 b = sb2[row * G + g];
             float2 v = make_float2(0.f, 0.f);
-            if (sidx < p.n_samples) v = make_float2((float)b.x - 127.5f, (float)b.y - 127.5f);
+            if (sidx < p.n_samples) {
+                v = make_float2((float)b.x - 127.5f, (float)b.y - 127.5f);
+            }
             r[u] = v;
         }
         __syncthreads();                                   // stage consumed (it is refilled one iteration later); exchange area free

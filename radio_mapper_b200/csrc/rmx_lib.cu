@@ -454,7 +454,8 @@ static int launch_argmax_tma(const rmx_plan* pl, const PassParams& pp, bool pre,
 }
 
 // forward pass 0 from cu8 through the persistent TMA-fed kernel; *taken = false when this plan / input cannot take it
-static int launch_fwd_tma(const rmx_plan* pl, const PassParams& pp, int cnt, cudaStream_t st, bool* taken) {
+static int launch_fwd_tma(const rmx_plan* pl, const PassParams& pp, int cnt, cudaStream_t st, bool* taken,
+                          const char* name = "col_fwd_cu8") {
     *taken = false;
     if (!pl->fwd_tma || pp.window != nullptr || pl->n_passes < 2) return RMX_OK;
     const TmaKernelEntry k = get_fwd_tma_kernel(pl->logn[0], pl->loge[0]);
@@ -465,13 +466,14 @@ static int launch_fwd_tma(const rmx_plan* pl, const PassParams& pp, int cnt, cud
     if ((unsigned long long)pl->n_samples % s != 0) return RMX_OK;       // whole rows only (no read past the last signal)
     const unsigned long long rows = (unsigned long long)pl->n_samples >> pl->logs[0];
     if (rows == 0 || ((reinterpret_cast<uintptr_t>(pp.cu8) | (uintptr_t)pp.cu8_stride) & 15) != 0) return RMX_OK;
-    if (2 * s > (1ULL << 32) - 1) return RMX_OK;
+    if (2 * s > (1ULL << 32) - 1 || (1u << k.logG) > 256u) return RMX_OK;
     CUtensorMap tmap;
-    const cuuint64_t gdim[3] = {2 * s, rows, (cuuint64_t)cnt};
+    // one UINT16 element = one (I, Q) byte pair, so a box row of G samples stays within the 256-element box limit
+    const cuuint64_t gdim[3] = {s, rows, (cuuint64_t)cnt};
     const cuuint64_t gstride[2] = {2 * s, (cuuint64_t)pp.cu8_stride};
-    const cuuint32_t box[3] = {(cuuint32_t)(2u << k.logG), (cuuint32_t)k.box_rows, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)(1u << k.logG), (cuuint32_t)k.box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(pp.cu8), gdim, gstride, box, estr,
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint8_t*>(pp.cu8), gdim, gstride, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RMX_ERR_CUDA, "cuTensorMapEncodeTiled (forward) failed (%d)", (int)r);
@@ -479,7 +481,7 @@ static int launch_fwd_tma(const rmx_plan* pl, const PassParams& pp, int cnt, cud
     const unsigned grid = std::min<unsigned>(n_tiles, (unsigned)k.ctas_per_sm * (unsigned)sm_count());
     CUDA_TRY(cudaFuncSetAttribute((const void*)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem_bytes));
     {
-        ProfScope prof(pl, "col_fwd_cu8", st);
+        ProfScope prof(pl, name, st);
         k.fn<<<grid, kThreads, k.smem_bytes, st>>>(pp, tmap, n_tiles);
     }
     LAUNCH_CHECK("col_fwd_cu8_tma");
@@ -1245,6 +1247,8 @@ extern "C" int rmx_welch_psd(rmx_plan* pl, const uint8_t* iq, float* psd, double
             for (int t = 0; t < np - 1; ++t) {
                 pp.tabs = pl->tabs[t];
                 pp.logS = pl->logs[t];
+                // (the persistent TMA-fed pass 0 measured SLOWER here: 0.228 against 0.193 ms for 1000 x 64k -- 16-point
+                // columns have no exchange to overlap the prefetch with, and 16000 small CTAs hide latency better)
                 rc = launch_pass(pl, get_col_kernel(pl->logn[t], pl->loge[t], t == 0 ? K_FWD_CU8 : K_FWD), "welch_col_fwd",
                                  dim3(tiles_of(pl, t, cnt)), pp, st);
                 if (rc) return rc;
@@ -1256,7 +1260,15 @@ extern "C" int rmx_welch_psd(rmx_plan* pl, const uint8_t* iq, float* psd, double
         pp.src = Y;
         pp.accum = accum;
         pp.tabs = pl->tabs[np - 1];
-        const KernelEntry k = get_contig_kernel(pl->logn[np - 1], pl->loge[np - 1], C_FWD_PSD);
+        KernelEntry k = get_contig_kernel(pl->logn[np - 1], pl->loge[np - 1], C_FWD_PSD);
+        // one row per tile: the next segment's row is prefetched by a bulk copy into a landing buffer behind the
+        // exchange area (needs 16-byte aligned rows)
+        if (pl->pair_prefetch && pl->logn[np - 1] == kLogThreads + pl->loge[np - 1] && np > 1 &&
+            (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
+            pp.prefetch = 1;
+            const size_t n = size_t(1) << pl->logn[np - 1];
+            k.smem_bytes = ((k.smem_bytes / sizeof(float2) + 15) & ~size_t(15)) * sizeof(float2) + n * sizeof(float2);
+        }
         const unsigned tiles_per_sig = (unsigned)std::max<long long>(1, (1LL << pl->logL) >> logtile);
         if ((1LL << pl->logL) < (1LL << logtile)) return fail(RMX_ERR_UNSUPPORTED, "Welch needs nperseg >= %d", 1 << logtile);
         // enough CTAs to fill the GPU twice over; each accumulates a chunk of segments in registers
