@@ -192,6 +192,30 @@ def main():
     with open(os.path.join(HERE, "tdoa.json"), "w") as f:
         json.dump(tdoa_json, f, indent=1)
 
+    # ---- the reference's own worked example (tdoa_processor.py:472-490): three buoys, dt = 150 000 / 300 000 ns ----
+    ex_buoys = [T.BuoyPosition("BUOY_ALPHA", 51.505, -0.09, 0.0, 50000),
+                T.BuoyPosition("BUOY_BETA", 51.51, -0.1, 0.0, 75000),
+                T.BuoyPosition("BUOY_GAMMA", 51.5, -0.12, 0.0, 60000)]
+    ex_proc = T.TDoAProcessor()
+    for b in ex_buoys:
+        ex_proc.register_buoy(b)
+    t0 = 1737217800000000000
+    ex_dets = [T.SignalDetection("BUOY_ALPHA", 121.5, -55, "2025-01-18T16:30:00Z", t0, 51.505, -0.09, 0.9, "emergency"),
+               T.SignalDetection("BUOY_BETA", 121.5, -60, "2025-01-18T16:30:00Z", t0 + 150000, 51.51, -0.1, 0.85, "emergency"),
+               T.SignalDetection("BUOY_GAMMA", 121.5, -58, "2025-01-18T16:30:00Z", t0 + 300000, 51.5, -0.12, 0.88, "emergency")]
+    ex_meas = ex_proc.tdoa_calculator.calculate_tdoa_measurements(ex_dets, ex_proc.buoy_positions)
+    with quiet:
+        ex_res = ex_proc.process_signal_detections(ex_dets)
+    example = dict(
+        buoys=[[b.buoy_id, b.lat, b.lng, b.altitude, b.timing_accuracy_ns] for b in ex_buoys],
+        base_time_ns=t0, sample_rate=2048000, frequency_mhz=121.5,
+        measurements=[[m.buoy1_id, m.buoy2_id, m.time_difference_ns, m.distance_difference_m, m.confidence, m.frequency_mhz]
+                      for m in ex_meas],
+        results=[dict(lat=r.estimated_lat, lng=r.estimated_lng, accuracy=r.accuracy_meters, confidence=r.confidence,
+                      signal_type=r.signal_type, contributing=sorted(r.contributing_buoys)) for r in ex_res])
+    with open(os.path.join(HERE, "example_main.json"), "w") as f:
+        json.dump(example, f, indent=1)
+
     # ---- (b) the drop-in surface: signatures and dataclass fields of the reference, as strings ----
     import dataclasses
     import inspect

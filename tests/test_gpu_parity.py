@@ -438,3 +438,39 @@ def test_subsample_delay_accuracy_vs_snr(rmx):
         assert np.max(np.abs(err)) < 0.5                       # always within half a sample of the truth
     assert rms[20] < 5e-3 and rms[0] < 5e-2 and rms[-10] < 0.3
     assert rms[20] < rms[0] < rms[-10]
+
+
+def test_reference_worked_example_from_iq(golden_dir):
+    """The reference's own worked example (tdoa_processor.py:472-490): three buoys whose detections are 150 000 and
+    300 000 ns apart.  tests/golden/example_main.json holds what the reference's calculate_tdoa_measurements makes
+    of those TIMESTAMPS; here the same arrival-time differences are put into synthetic cu8 IQ (307.2 and 614.4
+    samples at 2.048 Msps) and measured by the GPU correlation path: same pairs, order, frequency and timing
+    confidence, time / distance differences equal to the reference's within the sub-sample accuracy of the lag
+    search -- the seam a10/a11 feed (tdoa_processor.py:166-170)."""
+    import torch
+    from radio_mapper_b200.tdoa_processor import TDOAProcessor, BuoyPosition
+    with open(os.path.join(golden_dir, "example_main.json")) as f:
+        ex = json.load(f)
+    fs = ex["sample_rate"]
+    dt_ns = [0, 150000, 300000]
+    true = [t * 1e-9 * fs for t in dt_ns]                                 # 0, 307.2, 614.4 samples
+    iq, _, _ = synth.delayed_buoys(77, 3, 1 << 20, sample_rate=fs, snr_db=20.0, max_delay=700,
+                                   delays=[int(np.floor(t)) for t in true], frac_delays=[t - np.floor(t) for t in true])
+    proc = TDOAProcessor()
+    ids = []
+    for b in ex["buoys"]:
+        proc.register_buoy(BuoyPosition(*b))
+        ids.append(b[0])
+    meas = proc.correlate_iq(torch.from_numpy(iq[:, None, :]).pin_memory(), ids, fs, ex["frequency_mhz"])
+    rec = proc.correlate_iq_records(torch.from_numpy(iq[:, None, :]).pin_memory())
+    assert len(meas) == len(ex["measurements"]) == 3
+    for m, coh, (b1, b2, dt, dd, conf, fmhz) in zip(meas, rec["coherence"][0], ex["measurements"]):
+        assert (m.buoy1_id, m.buoy2_id, m.frequency_mhz) == (b1, b2, fmhz)
+        assert isinstance(m.time_difference_ns, int)
+        assert abs(m.time_difference_ns - dt) <= 10                      # 10 ns = 0.02 samples
+        assert abs(m.distance_difference_m - dd) <= 3.0                  # 10 ns of light
+        assert m.distance_difference_m == (m.time_difference_ns / 1e9) * 299792458.0      # :169-170 verbatim
+        # confidence = strength term x the reference's timing term (:200-210); the reference's strength term is
+        # min(c_i, c_j) of the detections, ours the measured coherence: the timing terms must be identical
+        ci = {"BUOY_ALPHA": 0.9, "BUOY_BETA": 0.85, "BUOY_GAMMA": 0.88}
+        assert abs(m.confidence / float(coh) - conf / min(ci[b1], ci[b2])) < 1e-6
