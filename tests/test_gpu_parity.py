@@ -474,3 +474,35 @@ def test_reference_worked_example_from_iq(golden_dir):
         # min(c_i, c_j) of the detections, ours the measured coherence: the timing terms must be identical
         ci = {"BUOY_ALPHA": 0.9, "BUOY_BETA": 0.85, "BUOY_GAMMA": 0.88}
         assert abs(m.confidence / float(coh) - conf / min(ci[b1], ci[b2])) < 1e-6
+
+
+def test_correlate_iq_edge_shapes():
+    """Host-facing call on degenerate shapes: no windows -> empty record table / no measurements; two buoys -> one
+    pair; the per-window generator (run_iter) hands back exactly the rows of run(); an unaligned (sliced) spectra
+    buffer takes the load path without the bulk-copy prefetch and returns the same records."""
+    import torch
+    from radio_mapper_b200 import engine
+    from radio_mapper_b200.tdoa_processor import TDOAProcessor
+    n = 1 << 17                                                        # plan 32 x 4096: X_i-stationary row pass
+    iq, d, _ = synth.delayed_buoys(5, 2, n)
+    proc = TDOAProcessor()
+    empty = proc.correlate_iq_records(torch.empty((2, 0, 2 * n), dtype=torch.uint8).pin_memory())
+    assert empty.shape == (0, 1)
+    assert proc.correlate_iq(torch.empty((2, 0, 2 * n), dtype=torch.uint8).pin_memory(), ["A", "B"]) == []
+    block = np.stack([iq, iq[::-1]], axis=1)                           # [B=2, W=2, 2N]; window 1 swaps the buoys
+    rec = proc.correlate_iq_records(torch.from_numpy(np.ascontiguousarray(block)).pin_memory())
+    assert rec.shape == (2, 1) and rec["lag"][0, 0] == d[1] - d[0] and rec["lag"][1, 0] == d[0] - d[1]
+    cor = proc._correlator(2, n, None)
+    rows = list(cor.run_iter(torch.from_numpy(np.ascontiguousarray(block)).cuda()))
+    assert len(rows) == 2 and all(np.array_equal(rows[w][f], rec[w][f]) for w in range(2) for f in ("lag", "peak", "frac"))
+    # spectra at an address that is 8- but not 16-byte aligned
+    plan = engine.Plan(2, n)
+    S = plan.forward(_cuda(iq))
+    pairs = _cuda(engine.pair_table(2))
+    a = engine.peaks_to_numpy(plan.xcorr_pairs_peak(S, pairs)).copy()
+    buf = torch.empty(S.numel() + 1, dtype=torch.complex64, device="cuda")
+    view = buf[1:].view(2, plan.fft_len)
+    view.copy_(S)
+    assert view.data_ptr() % 16 == 8
+    b = engine.peaks_to_numpy(plan.xcorr_pairs_peak(view, pairs))
+    assert np.array_equal(a, b)
