@@ -84,7 +84,10 @@ RMX_API int rmx_plan_create(rmx_plan** plan, int n_signals, size_t n_samples, si
  * X_i-stationary row pass; "pair_prefetch" = 0 | 1 next X_j row by bulk copy into shared memory;
  * "fwd_group_bytes" = forward passes run over groups of signals whose spectra fit this many bytes, so a pass
  * reads the previous one's output from L2 (0 = all signals per launch); "welch_clusters" = resident clusters of
- * the Welch kernel (0 = occupancy query); "fwd_tma" = 1 | 0 forward pass 0 through the persistent kernel that stages
+ * the Welch kernel (0 = occupancy query); "fuse_outer" = 0 | 1 three-pass plans (fft_len > 2^23): middle and outer inverse pass + arg-max as separate
+ * launches through the workspace (default) or in one persistent kernel through an L2-resident scratch ring (measured
+ * slightly slower on B200: see DESIGN.md);
+ * "fwd_tma" = 1 | 0 forward pass 0 through the persistent kernel that stages
  * the raw cu8 tiles in shared memory by 3-D TMA box loads (default; taken for whole-row windows and 16-byte aligned
  * input, otherwise -- and with 0 -- the per-thread 128-bit staging kernel runs). */
 RMX_API int rmx_plan_set_option(rmx_plan* plan, const char* name, long long value);

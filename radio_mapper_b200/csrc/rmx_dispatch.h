@@ -1,6 +1,7 @@
 // rmx_dispatch.h — lookup of the template-instantiated pass kernels (internal).
 #pragma once
 #include "rmx_kernels.cuh"
+#include "rmx_fused_outer.cuh"
 
 namespace rmx {
 
@@ -25,6 +26,15 @@ TmaKernelEntry get_argmax_tma_kernel(int logn, int loge, bool pre_twiddled);
 
 // persistent TMA-fed forward pass 0 from cu8 (n = 512, 1024 with 32 values per thread; n = 128, 256 with 16)
 TmaKernelEntry get_fwd_tma_kernel(int logn, int loge);
+
+// three-pass plans: middle + outer inverse pass + arg-max fused through an L2-resident scratch ring
+typedef void (*FusedOuterKernel)(const FusedOuterParams);
+struct FusedOuterEntry {
+    FusedOuterKernel fn;     // nullptr if (logn1, logn0) is not instantiated
+    size_t smem_bytes;
+    int logG1, logG0;
+};
+FusedOuterEntry get_fused_outer_kernel(int logn1, int logn0);
 
 // X_i-stationary pair pass (one row per tile, 16 values per thread: n = 4096); run = pairs per CTA
 struct PairRunEntry {

@@ -59,4 +59,21 @@ TmaKernelEntry get_argmax_tma_kernel16(int logn, bool pre) {
     }
 }
 
+template <int LOGN1, int LOGN0>
+static FusedOuterEntry fused_entry() {
+    using GEO1 = TileGeom<LOGN1, 4, true>;
+    using GEO0 = TileGeom<LOGN0, 4, true>;
+    return FusedOuterEntry{(FusedOuterKernel)k_outer_fused<LOGN1, LOGN0>,
+                           GEO1::SMEM_BYTES > GEO0::SMEM_BYTES ? GEO1::SMEM_BYTES : GEO0::SMEM_BYTES, GEO1::LOGG, GEO0::LOGG};
+}
+
+FusedOuterEntry get_fused_outer_kernel(int logn1, int logn0) {
+    if (logn1 == 8 && logn0 == 7) return fused_entry<8, 7>();      // L = 2^27 (cfg5)
+    if (logn1 == 7 && logn0 == 7) return fused_entry<7, 7>();      // L = 2^26
+    if (logn1 == 7 && logn0 == 6) return fused_entry<7, 6>();      // L = 2^25
+    if (logn1 == 6 && logn0 == 6) return fused_entry<6, 6>();      // L = 2^24
+    if (logn1 == 8 && logn0 == 8) return fused_entry<8, 8>();      // L = 2^28
+    return FusedOuterEntry{nullptr, 0, 0, 0};
+}
+
 }  // namespace rmx

@@ -81,6 +81,9 @@ struct rmx_plan {
     long long fwd_group_bytes = 0;    // forward passes run over groups of signals whose spectra fit this many bytes (0 = all at once)
     int welch_clusters = 0;           // resident clusters of the Welch kernel (0 = occupancy query)
     int fwd_tma = 1;                  // forward pass 0 through the persistent TMA-fed kernel (measured -10..-15 % on that pass)
+    int fuse_outer = 0;               // three-pass plans: middle + outer inverse pass fused through an L2-resident scratch ring
+                                      // (off: measured 17.0 ms against 16.0 ms for the separate launches at cfg5 -- the scratch
+                                      // stays in L2 as intended, but both passes are FMA/L1-bound at the same cost per tile)
 };
 
 static int build_stage_tables(rmx_plan* pl, int logn, int loge, StageTables* out) {
@@ -261,12 +264,28 @@ static WindowMode window_mode(const rmx_plan* pl, int n_pairs) {
     return w;
 }
 
+// three-pass plans whose two outer passes run fused (rmx_fused_outer.cuh): scratch ring + counters behind the partials
+constexpr int kFusedRingSlots = 10, kFusedLag = 4;   // ~3.5 slabs in flight with 444 CTAs x 2 tiles: lag past them, ring past the lag
+static FusedOuterEntry fused_outer_entry(const rmx_plan* pl) {
+    if (pl->n_passes != 3 || !pl->fuse_outer || pl->loge[0] != 4 || pl->loge[1] != 4) return FusedOuterEntry{nullptr, 0, 0, 0};
+    const FusedOuterEntry k = get_fused_outer_kernel(pl->logn[1], pl->logn[0]);
+    if (k.fn && pl->logn[2] < k.logG1) return FusedOuterEntry{nullptr, 0, 0, 0};
+    return k;
+}
+static size_t fused_outer_extra_bytes(const rmx_plan* pl) {
+    const FusedOuterEntry k = fused_outer_entry(pl);
+    if (!k.fn) return 0;
+    const size_t slab = (size_t(1) << (pl->logn[0] + pl->logn[1] + k.logG1)) * sizeof(float2);
+    return (size_t)kFusedRingSlots * slab + 1024;
+}
+
 extern "C" size_t rmx_plan_workspace_bytes(const rmx_plan* pl, int n_pairs) {
     if (!pl || n_pairs <= 0) return 0;
     const WindowMode w = window_mode(pl, n_pairs);
     if (w.mode >= 0) return (size_t)n_pairs * (w.n_chunks + 1) * w.slots * sizeof(float2) + 256;
     const size_t L = size_t(1) << pl->logL;
-    return (size_t)n_pairs * (L * sizeof(float2) + (size_t)tiles_per_item_pass0(pl) * sizeof(Partial)) + 256;
+    return (size_t)n_pairs * (L * sizeof(float2) + (size_t)tiles_per_item_pass0(pl) * sizeof(Partial)) + 1024 +
+           fused_outer_extra_bytes(pl);
 }
 
 extern "C" int rmx_plan_set_option(rmx_plan* pl, const char* name, long long value) {
@@ -276,6 +295,7 @@ extern "C" int rmx_plan_set_option(rmx_plan* pl, const char* name, long long val
     else if (!strcmp(name, "fwd_group_bytes")) pl->fwd_group_bytes = value < 0 ? 0 : value;
     else if (!strcmp(name, "welch_clusters")) pl->welch_clusters = (int)std::max<long long>(0, value);
     else if (!strcmp(name, "fwd_tma")) pl->fwd_tma = value != 0;
+    else if (!strcmp(name, "fuse_outer")) pl->fuse_outer = value != 0;
     else return fail(RMX_ERR_ARG, "unknown plan option '%s'", name);
     return RMX_OK;
 }
@@ -679,6 +699,78 @@ __global__ void __launch_bounds__(128) k_finalize_sum(const Partial* __restrict_
     }
 }
 
+// three-pass plans with fused outer passes: the middle-pass output never reaches the workspace, so c[m-1], c[m],
+// c[m+1] are evaluated from the ROW-pass output R (pre-twiddled for the middle pass):
+//     c[m] = 1/L * sum_{k0 < n0} sum_{k1 < n1}  w_L^{k0*m} * w_{n1}^{k1*m1} * R[(k0*n1 + k1)*n2 + col],
+//     m = m0*(n1*n2) + m1*n2 + col      (n0*n1 direct terms per lag: 32768 at cfg5, three lags per pair)
+__global__ void __launch_bounds__(256) k_finalize_sum2(const Partial* __restrict__ partials, int tiles_per_item,
+                                                       const float2* __restrict__ R, int logL, int logn0, int logn1, int logn2,
+                                                       int lag_pos_max, int lag_neg_max, float scale, rmx_peak* __restrict__ out) {
+    __shared__ float s_v[8];
+    __shared__ uint32_t s_l[8];
+    __shared__ float2 s_sum[8];
+    const int item = blockIdx.x;
+    float bv = -1.f;
+    uint32_t brank = 0xffffffffu;
+    for (int t = threadIdx.x; t < tiles_per_item; t += blockDim.x) {
+        const Partial p = partials[(long long)item * tiles_per_item + t];
+        if (p.val >= 0.f && better(p.val, p.rank, bv, brank)) { bv = p.val; brank = p.rank; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const uint32_t ol = __shfl_xor_sync(0xffffffffu, brank, off);
+        if (better(ov, ol, bv, brank)) { bv = ov; brank = ol; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_l[threadIdx.x >> 5] = brank; }
+    __syncthreads();
+    bv = s_v[0]; brank = s_l[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) if (better(s_v[w], s_l[w], bv, brank)) { bv = s_v[w]; brank = s_l[w]; }
+    const int blag = (int)brank - lag_neg_max;
+
+    const long long L = 1LL << logL;
+    const int n_terms = 1 << (logn0 + logn1);
+    const float2* __restrict__ Rp = R + ((long long)item << logL);
+    float y[3];
+    for (int d = -1; d <= 1; ++d) {
+        const long long lag = (long long)blag + d;
+        float2 acc = make_float2(0.f, 0.f);
+        const bool in_range = (lag >= -(long long)lag_neg_max) && (lag <= (long long)lag_pos_max);
+        if (in_range) {
+            const unsigned long long m = (unsigned long long)(lag < 0 ? lag + L : lag);
+            const unsigned long long col = m & ((1ULL << logn2) - 1ULL);
+            const unsigned long long m1 = (m >> logn2) & ((1ULL << logn1) - 1ULL);
+            for (int t = threadIdx.x; t < n_terms; t += blockDim.x) {
+                const unsigned long long k0 = (unsigned long long)t >> logn1, k1 = (unsigned long long)t & ((1ULL << logn1) - 1ULL);
+                const float2 v = Rp[((long long)t << logn2) + (long long)col];            // t = k0*n1 + k1
+                const float2 w0 = unit_root((uint32_t)((k0 * m) & (unsigned long long)(L - 1)), logL, true);
+                const float2 w1 = unit_root((uint32_t)((k1 * m1) & ((1ULL << logn1) - 1ULL)), logn1, true);
+                const float2 tt = cmul(cmul(v, w1), w0);
+                acc.x += tt.x; acc.y += tt.y;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        float2 tot = make_float2(0.f, 0.f);
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { tot.x += s_sum[w].x; tot.y += s_sum[w].y; }
+        y[d + 1] = in_range ? sqrtf(tot.x * tot.x + tot.y * tot.y) * scale : -1.f;
+    }
+    if (threadIdx.x == 0) {
+        rmx_peak r;
+        r.lag = blag;
+        r.peak = y[1];
+        r.frac = (y[0] >= 0.f && y[2] >= 0.f) ? parabolic(y[0], y[1], y[2]) : 0.f;
+        r.pad = bv;
+        out[item] = r;
+    }
+}
+
 // single-pass plans: the workspace already holds c in natural order
 __global__ void __launch_bounds__(128) k_finalize_direct(const float2* __restrict__ C, int logL, int lag_pos_max,
                                                          int lag_neg_max, rmx_peak* __restrict__ out) {
@@ -826,12 +918,19 @@ extern "C" int rmx_xcorr_pairs_peak(const rmx_plan* pl, const rmx_complex64* spe
     const size_t L = size_t(1) << pl->logL;
     const int tpi = tiles_per_item_pass0(pl);
     const size_t per_pair = L * sizeof(float2) + (size_t)tpi * sizeof(Partial);
-    if (workspace_bytes < per_pair + 256)
+    // the fused outer passes need the inter-pass twiddles on the row-pass output (the default placement)
+    FusedOuterEntry fused = twiddle_in_contig(pl) ? fused_outer_entry(pl) : FusedOuterEntry{nullptr, 0, 0, 0};
+    size_t extra = fused.fn ? fused_outer_extra_bytes(pl) : 0;
+    if (fused.fn && workspace_bytes < per_pair + 1024 + extra) { fused.fn = nullptr; extra = 0; }    // small caller workspace: unfused passes
+    if (workspace_bytes < per_pair + 1024 + extra)
         return fail(RMX_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one pair (%zu needed)", workspace_bytes,
-                    per_pair + 256);
-    const int chunk = (int)std::min<size_t>((size_t)n_pairs, (workspace_bytes - 256) / per_pair);
+                    per_pair + 1024 + extra);
+    const int chunk = (int)std::min<size_t>((size_t)n_pairs, (workspace_bytes - 1024 - extra) / per_pair);
     float2* D = reinterpret_cast<float2*>(workspace);
     Partial* partials = reinterpret_cast<Partial*>(reinterpret_cast<char*>(workspace) + (((size_t)chunk * L * sizeof(float2) + 255) & ~size_t(255)));
+    char* after_partials = reinterpret_cast<char*>(partials) + (((size_t)chunk * tpi * sizeof(Partial) + 255) & ~size_t(255));
+    unsigned* fused_counters = reinterpret_cast<unsigned*>(after_partials);
+    float2* fused_scratch = reinterpret_cast<float2*>(after_partials + 1024);
     const int np = pl->n_passes;
 
     for (int first = 0; first < n_pairs; first += chunk) {
@@ -852,6 +951,40 @@ extern "C" int rmx_xcorr_pairs_peak(const rmx_plan* pl, const rmx_complex64* spe
         set_post_twiddle(pl, &pp);
         int rc = launch_pair_pass(pl, pp, cnt, st);
         if (rc) return rc;
+        if (fused.fn) {
+            // three-pass plan: middle + outer pass + arg-max in one persistent kernel (rmx_fused_outer.cuh)
+            FusedOuterParams fp;
+            memset(&fp, 0, sizeof(fp));
+            fp.src = D;
+            fp.scratch = fused_scratch;
+            fp.partials = partials;
+            fp.counters = fused_counters;
+            fp.tabs1 = pl->tabs[1];
+            fp.tabs0 = pl->tabs[0];
+            fp.n_pairs = cnt;
+            fp.logL = pl->logL;
+            fp.logn2 = pl->logn[2];
+            fp.lag_pos_max = (int)pl->lag_pos_max;
+            fp.lag_neg_max = (int)pl->lag_neg_max;
+            fp.ring_slots = kFusedRingSlots;
+            fp.f_lag = kFusedLag;
+            fp.scale = inv_len;
+            CUDA_TRY(cudaMemsetAsync(fused_counters, 0, (1 + 2 * kFusedRingSlots) * sizeof(unsigned), st));
+            if (fused.smem_bytes > 48 * 1024)
+                CUDA_TRY(cudaFuncSetAttribute((const void*)fused.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused.smem_bytes));
+            {
+                ProfScope prof(pl, "outer_fused_argmax", st);
+                fused.fn<<<3 * sm_count(), kThreads, fused.smem_bytes, st>>>(fp);
+            }
+            LAUNCH_CHECK("outer_fused_argmax");
+            {
+                ProfScope prof(pl, "finalize_sum", st);
+                k_finalize_sum2<<<cnt, 256, 0, st>>>(partials, tpi, D, pl->logL, pl->logn[0], pl->logn[1], pl->logn[2],
+                                                     (int)pl->lag_pos_max, (int)pl->lag_neg_max, inv_len, out + first);
+            }
+            LAUNCH_CHECK("finalize_sum2");
+            continue;
+        }
         for (int t = np - 2; t >= 0; --t) {
             pp.tabs = pl->tabs[t];
             pp.logS = pl->logs[t];

@@ -506,3 +506,37 @@ def test_correlate_iq_edge_shapes():
     assert view.data_ptr() % 16 == 8
     b = engine.peaks_to_numpy(plan.xcorr_pairs_peak(view, pairs))
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("log_n", [23, 24])
+def test_fused_outer_passes_match_unfused(rmx, log_n):
+    """Three-pass plans (L = 2^24: 64 x 64 x 4096, L = 2^25: 64 x 128 x 4096): the fused middle + outer pass
+    (`fuse_outer`, slabs through an L2-resident scratch ring, arg-max on the fly, peak values from the row-pass
+    output) against the separate launches through the workspace -- same lags, peaks and offsets inside the
+    north_star tolerances of each other and of the generator / oracle; also with a restricted lag range (the
+    masked arg-max) and with the pairs walked in chunks (ring and counters reused across launches)."""
+    import torch
+    n = 1 << log_n
+    iq, delays = synth.delayed_buoys_torch(600 + log_n, 3, 1, n, torch.device("cuda"))
+    pairs_h = rmx.pair_table(3)
+    pairs = _cuda(pairs_h)
+    want = delays[0, pairs_h[:, 1]] - delays[0, pairs_h[:, 0]]
+    res = {}
+    for name, opts in (("fused", {"fuse_outer": 1}), ("unfused", {"fuse_outer": 0})):
+        plan = rmx.Plan(3, n, options=opts)
+        assert len(plan.pass_lengths) == 3
+        S = plan.forward(iq[:, 0, :])
+        res[name] = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, pairs)).copy()
+        res[name + "_chunked"] = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, pairs, max_pairs_in_flight=1)).copy()
+        plan.set_max_lag(5000)
+        plan.set_search_mode(True)                                  # full inverse + masked arg-max, not the one-pass search
+        res[name + "_lag5000"] = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, pairs)).copy()
+        del plan
+    assert np.array_equal(res["fused"]["lag"], want)
+    for key in ("", "_chunked", "_lag5000"):
+        _check_records(res["fused" + key], res["unfused" + key])
+    assert np.array_equal(res["fused"]["lag"], res["fused_chunked"]["lag"])
+    assert np.array_equal(res["fused"]["peak"], res["fused_chunked"]["peak"])
+    if log_n == 23:                                                  # one pair against the CPU oracle (2^24-point correlation)
+        ref = oracle.xcorr_pairs_peak(iq[:2, 0, :].cpu().numpy())
+        _check_records(res["fused"][:1], ref)
