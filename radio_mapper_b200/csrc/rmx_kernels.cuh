@@ -44,6 +44,9 @@
 #ifndef RMX_PAIR_TWTREE
 #define RMX_PAIR_TWTREE 1   // row passes and forward column passes: build stage twiddles from their power-of-two entries
 #endif
+#ifndef RMX_PAIR_SPLIT
+#define RMX_PAIR_SPLIT 1      // X_i-stationary row pass: split-phase exchange barriers (rmx_fft_split.cuh)
+#endif
 #ifndef RMX_PAIR_RUN_CTAS
 #define RMX_PAIR_RUN_CTAS 3   // resident CTAs per SM for the X_i-stationary pair pass
 #endif
@@ -163,6 +166,10 @@ __device__ __forceinline__ void bulk_load_1d(void* sdst, const void* gsrc, uint3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+
+}  // namespace rmx
+#include "rmx_fft_split.cuh"
+namespace rmx {
 
 
 __device__ __forceinline__ float2 load_cu8_sample(const uint8_t* base, long long idx) {
@@ -744,6 +751,12 @@ __global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run
     const int first = (int)blk * RUN;
     const int last = min(first + RUN, p.n_items);
     uint32_t parity = 0;
+#if RMX_PAIR_SPLIT
+    __shared__ __align__(8) unsigned long long s_split[2];
+    SplitBarriers sb;
+    split_init(sb, s_split);
+    if constexpr (!PREFETCH) __syncthreads();                 // (the prefetch path has its own barrier below)
+#endif
     // w_M^{row*i0} (times the scale): the same for every pair of the run -- one sincospif per CTA walk, not per pair
     const float2 tw_base = p.post_logm > 0 ? row_twiddle_base<E>(rr, (uint32_t)i0, p.post_logm, true, p.post_scale) : make_float2(1.f, 0.f);
     if constexpr (PREFETCH) {
@@ -781,12 +794,18 @@ __global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run
             const float2* __restrict__ xj = p.spectra + ((long long)pr.y << p.logL) + (row << LOGN);
 #pragma unroll
             for (int u = 0; u < E; ++u) r[u] = cmul_conj(RMX_X_LOAD(xj + i0 + u * NT), a[u]);     // X_j * conj(X_i)
+#if !RMX_PAIR_SPLIT
             if (pidx != first) {
                 if (RMX_PAIR_RUN_BULK_STORE && threadIdx.x == 0) bulk_store_wait_read();   // previous row has left the buffer
                 __syncthreads();
             }
+#endif
         }
+#if RMX_PAIR_SPLIT
+        fft_tile_split<GEO, true>(r, smem, g, i0, p.tabs, sb);      // the FREE barrier protects the exchange area across pairs
+#else
         fft_tile<GEO, true, (RMX_PAIR_TWTREE != 0)>(r, smem, g, i0, p.tabs);
+#endif
         if (p.post_logm > 0) {
             float2 tw[E];
             row_twiddles_from_base<E>(tw, tw_base, s_pw);
