@@ -78,6 +78,7 @@ RMX_API int rmx_unpack_cu8(const uint8_t* in, rmx_complex64* out, size_t n_sampl
 #define RMX_PLAN_NO_TMA           0x02u  /* arg-max pass through per-thread strided loads instead of the TMA-fed kernel */
 #define RMX_PLAN_NO_PAIR_RUN      0x04u  /* one pair per CTA in the 4096-point row pass (no X_i-stationary walk) */
 #define RMX_PLAN_NO_WELCH_CLUSTER 0x08u  /* Welch PSD through the two-pass path even where the cluster kernel applies */
+#define RMX_PLAN_ROW_E8           0x10u  /* two-pass plans on 2048-point rows held 8 values per thread (more resident CTAs) */
 #define RMX_PLAN_ROW_LOGN(n)      (((unsigned)(n) & 0x1fu) << 8)  /* force log2 of the row length of multi-pass plans */
 RMX_API int rmx_plan_create(rmx_plan** plan, int n_signals, size_t n_samples, size_t fft_len, unsigned flags);
 /* Tuning knobs (defaults are the measured best on B200): "pair_run" = 8 | 16 pairs walked by one CTA of the
@@ -89,7 +90,11 @@ RMX_API int rmx_plan_create(rmx_plan** plan, int n_signals, size_t n_samples, si
  * slightly slower on B200: see DESIGN.md);
  * "fwd_tma" = 1 | 0 forward pass 0 through the persistent kernel that stages
  * the raw cu8 tiles in shared memory by 3-D TMA box loads (default; taken for whole-row windows and 16-byte aligned
- * input, otherwise -- and with 0 -- the per-thread 128-bit staging kernel runs). */
+ * input, otherwise -- and with 0 -- the per-thread 128-bit staging kernel runs).
+ * Measured-slower alternatives of the 4096-point row pass, kept selectable for A/B runs:
+ * "pair_store" = 0 | 1 finished rows leave through a staging buffer + one bulk copy instead of per-thread stores;
+ * "pair_groups" = 0 | 2 | 3 one CTA of 2 or 3 warp groups that hand the FP32 pipe round on a ring of named barriers
+ * instead of independent CTAs; "pair_ctas" = 4 | 5 | 6 resident CTAs per SM of the RMX_PLAN_ROW_E8 row kernel. */
 RMX_API int rmx_plan_set_option(rmx_plan* plan, const char* name, long long value);
 RMX_API int rmx_plan_destroy(rmx_plan* plan);
 /* number of passes and their lengths n_t (outermost first); returns n_passes */

@@ -52,7 +52,7 @@ SIGNATURES = {
 }
 
 # plan flags (include/rmx.h)
-PLAN_TWIDDLE_IN_COL, PLAN_NO_TMA, PLAN_NO_PAIR_RUN, PLAN_NO_WELCH_CLUSTER = 0x01, 0x02, 0x04, 0x08
+PLAN_TWIDDLE_IN_COL, PLAN_NO_TMA, PLAN_NO_PAIR_RUN, PLAN_NO_WELCH_CLUSTER, PLAN_ROW_E8 = 0x01, 0x02, 0x04, 0x08, 0x10
 
 
 def plan_row_logn(n: int) -> int:

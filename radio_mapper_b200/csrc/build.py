@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "librmx.so")
 OBJ = os.path.join(HERE, "_obj")
-SOURCES = ["rmx_lib.cu", "rmx_inst_contig.cu", "rmx_inst_col.cu", "rmx_inst_contig32.cu", "rmx_inst_col32.cu"]
-HEADERS = ["rmx_fft_core.cuh", "rmx_kernels.cuh", "rmx_dispatch.h", os.path.join("..", "..", "include", "rmx.h")]
+SOURCES = ["rmx_lib.cu", "rmx_inst_contig.cu", "rmx_inst_col.cu", "rmx_inst_contig32.cu", "rmx_inst_col32.cu", "rmx_inst_contig8.cu"]
+HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "rmx.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-diag-suppress", "177"]

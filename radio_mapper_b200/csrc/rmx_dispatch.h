@@ -42,7 +42,11 @@ struct PairRunEntry {
     size_t smem_bytes;
     int run;
 };
-PairRunEntry get_pair_run_kernel(int logn, int loge, int run, bool prefetch);
+// (ctas: resident CTAs per SM the 2048-point variant is compiled for: 4, 5 or 6)
+PairRunEntry get_pair_run_kernel(int logn, int loge, int run, int mem, int ctas = 0);
+// the same pass with `groups` (2 or 3) warp groups per CTA that hand the FP32 pipe round (rmx_pair_pp.cuh);
+// launch with groups * 256 threads, smem_bytes covers all groups
+PairRunEntry get_pair_run_pp_kernel(int logn, int loge, int run, int groups);
 
 typedef void (*WelchClusterKernel)(const WelchClusterParams);
 struct WelchClusterEntry {

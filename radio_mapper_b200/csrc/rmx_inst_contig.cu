@@ -27,8 +27,12 @@ static KernelEntry contig_by_logn(int logn) {
 
 KernelEntry get_contig_kernel32(int logn, int mode);   // rmx_inst_contig32.cu
 
+KernelEntry get_contig_kernel8(int logn, int mode);    // rmx_inst_contig8.cu
+PairRunEntry get_pair_run_kernel8(int run, int mem, int ctas);
+
 KernelEntry get_contig_kernel(int logn, int loge, int mode) {
     if (loge == 5) return get_contig_kernel32(logn, mode);
+    if (loge == 3) return get_contig_kernel8(logn, mode);
     if (loge != 4) return KernelEntry{nullptr, 0, 0};
     switch (mode) {
         case C_FWD: return contig_by_logn<4, C_FWD>(logn);
@@ -42,19 +46,36 @@ KernelEntry get_contig_kernel(int logn, int loge, int mode) {
     }
 }
 
-template <int RUN, bool PREFETCH>
+template <int RUN, bool PREFETCH, bool STAGED>
 static PairRunEntry pair_run_entry() {
     using GEO = TileGeom<12, 4, false>;
     const size_t exchange = size_t((GEO::NP + 15) & ~15) * sizeof(float2);
-    return PairRunEntry{(PassKernel)k_contig_pair_run<12, 4, RUN, PREFETCH>,
-                        PREFETCH ? exchange + size_t(GEO::N) * sizeof(float2) : GEO::SMEM_BYTES, RUN};
+    return PairRunEntry{(PassKernel)k_contig_pair_run<12, 4, RUN, PREFETCH, STAGED>,
+                        (PREFETCH || STAGED) ? exchange + size_t(GEO::N) * sizeof(float2) : GEO::SMEM_BYTES, RUN};
 }
 
-// run: pairs walked by one CTA (8 or 16); prefetch: next X_j row through a bulk copy into shared memory
-PairRunEntry get_pair_run_kernel(int logn, int loge, int run, bool prefetch) {
+// run: pairs walked by one CTA (8 or 16); mem: 0 = per-thread loads and stores, 1 = next X_j row prefetched by a bulk
+// copy into shared memory, 2 = finished row staged in shared memory and stored by a bulk copy
+PairRunEntry get_pair_run_kernel(int logn, int loge, int run, int mem, int ctas) {
+    if (logn == 11 && loge == 3) return get_pair_run_kernel8(run, mem == 2 ? 0 : mem, ctas);
     if (logn == 12 && loge == 4) {
-        if (run >= 16) return prefetch ? pair_run_entry<16, true>() : pair_run_entry<16, false>();
-        return prefetch ? pair_run_entry<8, true>() : pair_run_entry<8, false>();
+        if (run >= 16) return mem == 1 ? pair_run_entry<16, true, false>() : mem == 2 ? pair_run_entry<16, false, true>() : pair_run_entry<16, false, false>();
+        return mem == 1 ? pair_run_entry<8, true, false>() : mem == 2 ? pair_run_entry<8, false, true>() : pair_run_entry<8, false, false>();
+    }
+    return PairRunEntry{nullptr, 0, 0};
+}
+
+template <int RUN, int NG>
+static PairRunEntry pair_run_pp_entry() {
+    using GEO = TileGeom<12, 4, false>;
+    const size_t group = (size_t((GEO::NP + 15) & ~15) + size_t(GEO::N)) * sizeof(float2);
+    return PairRunEntry{(PassKernel)k_contig_pair_run_pp<12, 4, RUN, NG>, NG * group, RUN};
+}
+
+PairRunEntry get_pair_run_pp_kernel(int logn, int loge, int run, int groups) {
+    if (logn == 12 && loge == 4) {
+        if (groups == 2) return run >= 16 ? pair_run_pp_entry<16, 2>() : pair_run_pp_entry<8, 2>();
+        if (groups == 3) return run >= 16 ? pair_run_pp_entry<16, 3>() : pair_run_pp_entry<8, 3>();
     }
     return PairRunEntry{nullptr, 0, 0};
 }

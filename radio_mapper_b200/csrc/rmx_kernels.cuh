@@ -44,6 +44,12 @@
 #ifndef RMX_PAIR_TWTREE
 #define RMX_PAIR_TWTREE 1   // row passes and forward column passes: build stage twiddles from their power-of-two entries
 #endif
+#ifndef RMX_DBG_PAIR_NOLOAD
+#define RMX_DBG_PAIR_NOLOAD 0    // timing experiments only: the row pass without its spectrum loads ...
+#endif
+#ifndef RMX_DBG_PAIR_NOSTORE
+#define RMX_DBG_PAIR_NOSTORE 0   // ... and / or without its workspace stores (results are wrong by construction)
+#endif
 #ifndef RMX_PAIR_SPLIT
 #define RMX_PAIR_SPLIT 1      // X_i-stationary row pass: split-phase exchange barriers (rmx_fft_split.cuh)
 #endif
@@ -217,7 +223,7 @@ __device__ __forceinline__ void block_argmax(float& v, uint32_t& rank, RankOf ra
 // ---------------------------------------------------------------------------------------
 // resident CTAs per SM the register allocator must leave room for: 32 values per thread need
 // ~128 registers (2 CTAs), 16 values per thread fit in 80 (3 CTAs)
-__host__ __device__ constexpr int min_ctas(int loge) { return loge >= 5 ? 2 : 3; }
+__host__ __device__ constexpr int min_ctas(int loge) { return loge >= 5 ? 2 : loge == 4 ? 3 : 4; }
 __host__ __device__ constexpr int argmax_tma_ctas(int loge) { return loge >= 5 ? RMX_ARGMAX_TMA_CTAS : 4; }
 
 template <int LOGN, int LOGE, int MODE>
@@ -725,8 +731,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(LOGE)) k_col_fwd_cu8_tma(co
 // PREFETCH: the X_j row of the NEXT pair of the run is brought into a 32 KB landing buffer by one bulk copy
 // (TMA engine, completes on an mbarrier) while the CTA transforms the current pair, so only the first pair of a
 // run waits for its spectrum row and no registers are tied up by loads in flight.
-template <int LOGN, int LOGE, int RUN, bool PREFETCH>
-__global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run(const PassParams p) {
+// STAGED (instead of PREFETCH; the same 32 KB buffer): the finished row leaves through a dedicated staging buffer and
+// ONE bulk copy (TMA engine) that drains while the CTA already transforms the next pair -- no burst of 16 global
+// stores per thread through the LSU queue that the next pair's shared-memory exchanges share.
+template <int LOGN, int LOGE, int RUN, bool PREFETCH, bool STAGED = false, int CTAS = RMX_PAIR_RUN_CTAS>
+__global__ void __launch_bounds__(kThreads, CTAS) k_contig_pair_run(const PassParams p) {
+    static_assert(!(PREFETCH && STAGED), "one 32 KB buffer: landing zone or store staging");
     using GEO = TileGeom<LOGN, LOGE, false>;
     constexpr int E = GEO::E, NT = GEO::NT;
     static_assert(GEO::G == 1 && GEO::NSTAGES >= 2, "one row per tile");
@@ -792,8 +802,14 @@ __global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run
             }
         } else {
             const float2* __restrict__ xj = p.spectra + ((long long)pr.y << p.logL) + (row << LOGN);
+#if RMX_DBG_PAIR_NOLOAD
+#pragma unroll
+            for (int u = 0; u < E; ++u) r[u] = cmul_conj(make_float2((float)(pidx + u), (float)(i0 - u)), a[u]);
+            (void)xj;
+#else
 #pragma unroll
             for (int u = 0; u < E; ++u) r[u] = cmul_conj(RMX_X_LOAD(xj + i0 + u * NT), a[u]);     // X_j * conj(X_i)
+#endif
 #if !RMX_PAIR_SPLIT
             if (pidx != first) {
                 if (RMX_PAIR_RUN_BULK_STORE && threadIdx.x == 0) bulk_store_wait_read();   // previous row has left the buffer
@@ -817,7 +833,17 @@ __global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run
             for (int u = 0; u < E; ++u) { r[u].x *= p.scale; r[u].y *= p.scale; }
         }
         float2* __restrict__ out = p.dst + (long long)pidx * p.src_item_stride + (row << LOGN);
-        if constexpr (RMX_PAIR_RUN_BULK_STORE && !PREFETCH) {
+        if constexpr (STAGED) {
+            if (pidx != first) {
+                if (threadIdx.x == 0) bulk_store_wait_read();        // the previous row has left the staging buffer (long ago)
+                __syncthreads();
+            }
+#pragma unroll
+            for (int u = 0; u < E; ++u) land[i0 + u * NT] = r[u];
+            fence_proxy_async();
+            __syncthreads();
+            if (threadIdx.x == 0) bulk_store_1d(out, land, ROW_BYTES);
+        } else if constexpr (RMX_PAIR_RUN_BULK_STORE && !PREFETCH) {
             // row -> exchange buffer -> one bulk copy (TMA engine); it drains while the next pair loads
             __syncthreads();                                 // every thread is past its last exchange read
 #pragma unroll
@@ -826,11 +852,18 @@ __global__ void __launch_bounds__(kThreads, RMX_PAIR_RUN_CTAS) k_contig_pair_run
             __syncthreads();
             if (threadIdx.x == 0) bulk_store_1d(out, smem, (uint32_t)(GEO::N * sizeof(float2)));
         } else {
+#if RMX_DBG_PAIR_NOSTORE
+            float chk = 0.f;
+#pragma unroll
+            for (int u = 0; u < E; ++u) chk += r[u].x * r[u].y;
+            if (chk == 1.2345e-30f) out[i0] = r[0];                  // keeps the arithmetic alive, never true in practice
+#else
 #pragma unroll
             for (int u = 0; u < E; ++u) RMX_D_STORE(out + i0 + u * NT, r[u]);
+#endif
         }
     }
-    if (RMX_PAIR_RUN_BULK_STORE && !PREFETCH && threadIdx.x == 0) bulk_store_wait_read();
+    if ((STAGED || (RMX_PAIR_RUN_BULK_STORE && !PREFETCH)) && threadIdx.x == 0) bulk_store_wait_read();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1102,3 +1135,4 @@ __global__ void __launch_bounds__(kThreads, argmax_tma_ctas(LOGE)) k_col_argmax_
 }
 
 }  // namespace rmx
+#include "rmx_pair_pp.cuh"

@@ -78,6 +78,9 @@ struct rmx_plan {
     // tuning knobs (rmx_plan_set_option)
     int pair_run = 8;                 // pairs walked by one CTA of the X_i-stationary row pass (8 or 16)
     int pair_prefetch = 1;            // next X_j row by bulk copy into shared memory
+    int pair_ctas = 5;                // resident CTAs per SM the 2048-point row pass (RMX_PLAN_ROW_E8) is compiled for: 4 | 5 | 6
+    int pair_groups = 0;              // 2 | 3: warp groups per CTA handing the FP32 pipe round (rmx_pair_pp.cuh); 0 = independent CTAs
+    int pair_store = 0;               // finished rows through a staging buffer + bulk copy (takes the prefetch buffer's place)
     long long fwd_group_bytes = 0;    // forward passes run over groups of signals whose spectra fit this many bytes (0 = all at once)
     int welch_clusters = 0;           // resident clusters of the Welch kernel (0 = occupancy query)
     int fwd_tma = 1;                  // forward pass 0 through the persistent TMA-fed kernel (measured -10..-15 % on that pass)
@@ -121,7 +124,8 @@ static int choose_col_loge(int logn) {
     if (ok32) return 5;
     return 0;
 }
-static int choose_contig_loge(int logn) {
+static int choose_contig_loge(int logn, unsigned flags = 0) {
+    if ((flags & RMX_PLAN_ROW_E8) && logn == max_contig_logn(3)) return 3;
     if (logn >= 4 && logn <= max_contig_logn(4)) return 4;
     if (logn == max_contig_logn(5)) return 5;
     return 0;
@@ -137,6 +141,7 @@ static int choose_passes(rmx_plan* pl) {
     if (logL - 12 >= 5 && logL - 12 <= maxk) maxc = 12;
     if (logL - 13 > maxk) maxc = 12;        // three passes: the 4096-point row kernels are ~15 % faster per element (cfg5)
     { const int e = (int)((pl->flags >> 8) & 0x1fu); if (e >= 8 && e <= max_contig_logn(5)) maxc = e; }   // RMX_PLAN_ROW_LOGN: developer override
+    if ((pl->flags & RMX_PLAN_ROW_E8) && logL - max_contig_logn(3) >= 5 && logL - max_contig_logn(3) <= maxk) maxc = max_contig_logn(3);
     if (logL < minn) return fail(RMX_ERR_UNSUPPORTED, "fft_len 2^%d is below the minimum 2^%d", logL, minn);
     if (logL <= maxc) {
         pl->n_passes = 1;
@@ -163,7 +168,7 @@ static int choose_passes(rmx_plan* pl) {
         if (pl->loge[t] == 0) return fail(RMX_ERR_UNSUPPORTED, "no pass split for fft_len 2^%d", logL);
     }
     pl->logn[ncol] = contig;
-    pl->loge[ncol] = choose_contig_loge(contig);
+    pl->loge[ncol] = choose_contig_loge(contig, pl->flags);
     pl->logs[ncol] = 0;
     pl->n_passes = ncol + 1;
     return RMX_OK;
@@ -292,6 +297,12 @@ extern "C" int rmx_plan_set_option(rmx_plan* pl, const char* name, long long val
     if (!pl || !name) return fail(RMX_ERR_ARG, "null argument to rmx_plan_set_option");
     if (!strcmp(name, "pair_run")) { if (value != 8 && value != 16) return fail(RMX_ERR_ARG, "pair_run must be 8 or 16"); pl->pair_run = (int)value; }
     else if (!strcmp(name, "pair_prefetch")) pl->pair_prefetch = value != 0;
+    else if (!strcmp(name, "pair_store")) pl->pair_store = value != 0;
+    else if (!strcmp(name, "pair_ctas")) pl->pair_ctas = (int)value;
+    else if (!strcmp(name, "pair_groups")) {
+        if (value != 0 && value != 2 && value != 3) return fail(RMX_ERR_ARG, "pair_groups must be 0, 2 or 3 (got %lld)", (long long)value);
+        pl->pair_groups = (int)value;
+    }
     else if (!strcmp(name, "fwd_group_bytes")) pl->fwd_group_bytes = value < 0 ? 0 : value;
     else if (!strcmp(name, "welch_clusters")) pl->welch_clusters = (int)std::max<long long>(0, value);
     else if (!strcmp(name, "fwd_tma")) pl->fwd_tma = value != 0;
@@ -514,10 +525,24 @@ static int launch_pair_pass(const rmx_plan* pl, const PassParams& pp, int cnt, c
     const int last = pl->n_passes - 1;
     // the bulk-copy prefetch needs 16-byte aligned spectrum rows (rows are multiples of 32 KB apart)
     const bool prefetch = pl->pair_prefetch != 0 && (reinterpret_cast<uintptr_t>(pp.spectra) & 15) == 0;
-    const PairRunEntry kr = get_pair_run_kernel(pl->logn[last], pl->loge[last], pl->pair_run, prefetch);
+    const bool staged = pl->pair_store != 0 && (reinterpret_cast<uintptr_t>(pp.dst) & 15) == 0;
+    const PairRunEntry kr = get_pair_run_kernel(pl->logn[last], pl->loge[last], pl->pair_run, staged ? 2 : prefetch ? 1 : 0, pl->pair_ctas);
     if (kr.fn && pl->n_passes >= 2 && !(pl->flags & RMX_PLAN_NO_PAIR_RUN)) {
         const long long rows = 1LL << (pl->logL - pl->logn[last]);
         const long long blocks = (cnt + kr.run - 1) / kr.run;
+        const PairRunEntry kg = (pl->pair_groups && prefetch && !staged)
+                                    ? get_pair_run_pp_kernel(pl->logn[last], pl->loge[last], pl->pair_run, pl->pair_groups)
+                                    : PairRunEntry{nullptr, 0, 0};
+        if (kg.fn) {
+            const long long vblocks = rows * ((cnt + kg.run - 1) / kg.run);
+            CUDA_TRY(cudaFuncSetAttribute((const void*)kg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kg.smem_bytes));
+            {
+                ProfScope prof(pl, "contig_inv_pair", st);
+                kg.fn<<<(unsigned)((vblocks + pl->pair_groups - 1) / pl->pair_groups), kThreads * pl->pair_groups, kg.smem_bytes, st>>>(pp);
+            }
+            LAUNCH_CHECK("contig_inv_pair_groups");
+            return RMX_OK;
+        }
         return launch_pass(pl, KernelEntry{kr.fn, kr.smem_bytes, 0}, "contig_inv_pair", dim3((unsigned)(rows * blocks)), pp, st);
     }
     return launch_pass(pl, get_contig_kernel(pl->logn[last], pl->loge[last], C_INV_PAIR), "contig_inv_pair",
