@@ -298,7 +298,10 @@ extern "C" int rmx_plan_set_option(rmx_plan* pl, const char* name, long long val
     if (!strcmp(name, "pair_run")) { if (value != 8 && value != 16) return fail(RMX_ERR_ARG, "pair_run must be 8 or 16"); pl->pair_run = (int)value; }
     else if (!strcmp(name, "pair_prefetch")) pl->pair_prefetch = value != 0;
     else if (!strcmp(name, "pair_store")) pl->pair_store = value != 0;
-    else if (!strcmp(name, "pair_ctas")) pl->pair_ctas = (int)value;
+    else if (!strcmp(name, "pair_ctas")) {
+        if (value < 4 || value > 6) return fail(RMX_ERR_ARG, "pair_ctas must be 4, 5 or 6 (got %lld)", (long long)value);
+        pl->pair_ctas = (int)value;
+    }
     else if (!strcmp(name, "pair_groups")) {
         if (value != 0 && value != 2 && value != 3) return fail(RMX_ERR_ARG, "pair_groups must be 0, 2 or 3 (got %lld)", (long long)value);
         pl->pair_groups = (int)value;
