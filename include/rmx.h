@@ -92,7 +92,8 @@ RMX_API int rmx_plan_create(rmx_plan** plan, int n_signals, size_t n_samples, si
  * the raw cu8 tiles in shared memory by 3-D TMA box loads (default; taken for whole-row windows and 16-byte aligned
  * input, otherwise -- and with 0 -- the per-thread 128-bit staging kernel runs).
  * Measured-slower alternatives of the 4096-point row pass, kept selectable for A/B runs:
- * "pair_store" = 0 | 1 finished rows leave through a staging buffer + one bulk copy instead of per-thread stores;
+ * "pair_store" = 0 | 1 | 2 finished rows leave by per-thread stores (default), through a dedicated staging buffer + one
+ * bulk copy (1: takes the prefetch buffer's place), or staged in the exchange buffer + one bulk copy (2: keeps the prefetch);
  * "pair_groups" = 0 | 2 | 3 one CTA of 2 or 3 warp groups that hand the FP32 pipe round on a ring of named barriers
  * instead of independent CTAs; "pair_ctas" = 4 | 5 | 6 resident CTAs per SM of the RMX_PLAN_ROW_E8 row kernel. */
 RMX_API int rmx_plan_set_option(rmx_plan* plan, const char* name, long long value);

@@ -46,7 +46,7 @@ KernelEntry get_contig_kernel(int logn, int loge, int mode) {
     }
 }
 
-template <int RUN, bool PREFETCH, bool STAGED>
+template <int RUN, bool PREFETCH, int STAGED>
 static PairRunEntry pair_run_entry() {
     using GEO = TileGeom<12, 4, false>;
     const size_t exchange = size_t((GEO::NP + 15) & ~15) * sizeof(float2);
@@ -55,12 +55,13 @@ static PairRunEntry pair_run_entry() {
 }
 
 // run: pairs walked by one CTA (8 or 16); mem: 0 = per-thread loads and stores, 1 = next X_j row prefetched by a bulk
-// copy into shared memory, 2 = finished row staged in shared memory and stored by a bulk copy
+// copy into shared memory, 2 = finished row staged in shared memory and stored by a bulk copy, 3 = prefetch + the
+// finished row staged in the exchange buffer and stored by a bulk copy
 PairRunEntry get_pair_run_kernel(int logn, int loge, int run, int mem, int ctas) {
-    if (logn == 11 && loge == 3) return get_pair_run_kernel8(run, mem == 2 ? 0 : mem, ctas);
+    if (logn == 11 && loge == 3) return get_pair_run_kernel8(run, mem == 1 || mem == 3 ? 1 : 0, ctas);
     if (logn == 12 && loge == 4) {
-        if (run >= 16) return mem == 1 ? pair_run_entry<16, true, false>() : mem == 2 ? pair_run_entry<16, false, true>() : pair_run_entry<16, false, false>();
-        return mem == 1 ? pair_run_entry<8, true, false>() : mem == 2 ? pair_run_entry<8, false, true>() : pair_run_entry<8, false, false>();
+        if (run >= 16) return mem == 1 ? pair_run_entry<16, true, 0>() : mem == 2 ? pair_run_entry<16, false, 1>() : mem == 3 ? pair_run_entry<16, true, 2>() : pair_run_entry<16, false, 0>();
+        return mem == 1 ? pair_run_entry<8, true, 0>() : mem == 2 ? pair_run_entry<8, false, 1>() : mem == 3 ? pair_run_entry<8, true, 2>() : pair_run_entry<8, false, 0>();
     }
     return PairRunEntry{nullptr, 0, 0};
 }

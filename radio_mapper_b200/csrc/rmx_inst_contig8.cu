@@ -22,7 +22,7 @@ template <int RUN, bool PREFETCH, int CTAS>
 static PairRunEntry pair_run8_entry() {
     using GEO = TileGeom<11, 3, false>;
     const size_t exchange = size_t((GEO::NP + 15) & ~15) * sizeof(float2);
-    return PairRunEntry{(PassKernel)k_contig_pair_run<11, 3, RUN, PREFETCH, false, CTAS>,
+    return PairRunEntry{(PassKernel)k_contig_pair_run<11, 3, RUN, PREFETCH, 0, CTAS>,
                         PREFETCH ? exchange + size_t(GEO::N) * sizeof(float2) : GEO::SMEM_BYTES, RUN};
 }
 

@@ -734,9 +734,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(LOGE)) k_col_fwd_cu8_tma(co
 // STAGED (instead of PREFETCH; the same 32 KB buffer): the finished row leaves through a dedicated staging buffer and
 // ONE bulk copy (TMA engine) that drains while the CTA already transforms the next pair -- no burst of 16 global
 // stores per thread through the LSU queue that the next pair's shared-memory exchanges share.
-template <int LOGN, int LOGE, int RUN, bool PREFETCH, bool STAGED = false, int CTAS = RMX_PAIR_RUN_CTAS>
+// STAGED == 2 (with PREFETCH): the finished row is staged in the EXCHANGE buffer (free between the last gather of a
+// pair and the first scatter of the next) and leaves by one bulk copy; the landing buffer keeps prefetching.
+template <int LOGN, int LOGE, int RUN, bool PREFETCH, int STAGED = 0, int CTAS = RMX_PAIR_RUN_CTAS>
 __global__ void __launch_bounds__(kThreads, CTAS) k_contig_pair_run(const PassParams p) {
-    static_assert(!(PREFETCH && STAGED), "one 32 KB buffer: landing zone or store staging");
+    static_assert(!(PREFETCH && STAGED == 1), "one 32 KB buffer: landing zone or store staging");
+    static_assert(STAGED != 2 || (PREFETCH && RMX_PAIR_SPLIT), "exchange-buffer staging rides on the prefetch path's barriers");
     using GEO = TileGeom<LOGN, LOGE, false>;
     constexpr int E = GEO::E, NT = GEO::NT;
     static_assert(GEO::G == 1 && GEO::NSTAGES >= 2, "one row per tile");
@@ -793,6 +796,9 @@ __global__ void __launch_bounds__(kThreads, CTAS) k_contig_pair_run(const PassPa
             parity ^= 1u;
 #pragma unroll
             for (int u = 0; u < E; ++u) r[u] = cmul_conj(land[i0 + u * NT], a[u]);            // X_j * conj(X_i)
+            if constexpr (STAGED == 2) {
+                if (threadIdx.x == 0 && pidx != first) bulk_store_wait_read();      // previous row has left the exchange buffer
+            }
             __syncthreads();          // landing buffer consumed; also: everyone is past the previous pair's last exchange read
             if (threadIdx.x == 0 && pidx + 1 < last) {
                 const int2 prn = __ldg(p.pairs + pidx + 1);
@@ -833,7 +839,20 @@ __global__ void __launch_bounds__(kThreads, CTAS) k_contig_pair_run(const PassPa
             for (int u = 0; u < E; ++u) { r[u].x *= p.scale; r[u].y *= p.scale; }
         }
         float2* __restrict__ out = p.dst + (long long)pidx * p.src_item_stride + (row << LOGN);
-        if constexpr (STAGED) {
+        if constexpr (STAGED == 2) {
+#if RMX_PAIR_SPLIT
+            if (sb.free_pending) {                            // every thread is past its last exchange read
+                mbar_wait(&sb.bar[1], sb.par_free);
+                sb.par_free ^= 1u;
+                sb.free_pending = false;
+            }
+#endif
+#pragma unroll
+            for (int u = 0; u < E; ++u) smem[i0 + u * NT] = r[u];
+            fence_proxy_async();
+            __syncthreads();
+            if (threadIdx.x == 0) bulk_store_1d(out, smem, ROW_BYTES);
+        } else if constexpr (STAGED == 1) {
             if (pidx != first) {
                 if (threadIdx.x == 0) bulk_store_wait_read();        // the previous row has left the staging buffer (long ago)
                 __syncthreads();
@@ -863,7 +882,7 @@ __global__ void __launch_bounds__(kThreads, CTAS) k_contig_pair_run(const PassPa
 #endif
         }
     }
-    if ((STAGED || (RMX_PAIR_RUN_BULK_STORE && !PREFETCH)) && threadIdx.x == 0) bulk_store_wait_read();
+    if ((STAGED != 0 || (RMX_PAIR_RUN_BULK_STORE && !PREFETCH)) && threadIdx.x == 0) bulk_store_wait_read();
 }
 
 // ---------------------------------------------------------------------------------------

@@ -297,7 +297,10 @@ extern "C" int rmx_plan_set_option(rmx_plan* pl, const char* name, long long val
     if (!pl || !name) return fail(RMX_ERR_ARG, "null argument to rmx_plan_set_option");
     if (!strcmp(name, "pair_run")) { if (value != 8 && value != 16) return fail(RMX_ERR_ARG, "pair_run must be 8 or 16"); pl->pair_run = (int)value; }
     else if (!strcmp(name, "pair_prefetch")) pl->pair_prefetch = value != 0;
-    else if (!strcmp(name, "pair_store")) pl->pair_store = value != 0;
+    else if (!strcmp(name, "pair_store")) {
+        if (value < 0 || value > 2) return fail(RMX_ERR_ARG, "pair_store must be 0, 1 or 2 (got %lld)", (long long)value);
+        pl->pair_store = (int)value;
+    }
     else if (!strcmp(name, "pair_ctas")) {
         if (value < 4 || value > 6) return fail(RMX_ERR_ARG, "pair_ctas must be 4, 5 or 6 (got %lld)", (long long)value);
         pl->pair_ctas = (int)value;
@@ -528,12 +531,14 @@ static int launch_pair_pass(const rmx_plan* pl, const PassParams& pp, int cnt, c
     const int last = pl->n_passes - 1;
     // the bulk-copy prefetch needs 16-byte aligned spectrum rows (rows are multiples of 32 KB apart)
     const bool prefetch = pl->pair_prefetch != 0 && (reinterpret_cast<uintptr_t>(pp.spectra) & 15) == 0;
-    const bool staged = pl->pair_store != 0 && (reinterpret_cast<uintptr_t>(pp.dst) & 15) == 0;
-    const PairRunEntry kr = get_pair_run_kernel(pl->logn[last], pl->loge[last], pl->pair_run, staged ? 2 : prefetch ? 1 : 0, pl->pair_ctas);
+    const bool dst_ok = (reinterpret_cast<uintptr_t>(pp.dst) & 15) == 0;
+    const bool staged = pl->pair_store == 1 && dst_ok;                       // dedicated staging buffer, no prefetch
+    const bool xstaged = pl->pair_store == 2 && dst_ok && prefetch;           // staged in the exchange buffer, with prefetch
+    const PairRunEntry kr = get_pair_run_kernel(pl->logn[last], pl->loge[last], pl->pair_run, xstaged ? 3 : staged ? 2 : prefetch ? 1 : 0, pl->pair_ctas);
     if (kr.fn && pl->n_passes >= 2 && !(pl->flags & RMX_PLAN_NO_PAIR_RUN)) {
         const long long rows = 1LL << (pl->logL - pl->logn[last]);
         const long long blocks = (cnt + kr.run - 1) / kr.run;
-        const PairRunEntry kg = (pl->pair_groups && prefetch && !staged)
+        const PairRunEntry kg = (pl->pair_groups && prefetch && !staged && !xstaged)
                                     ? get_pair_run_pp_kernel(pl->logn[last], pl->loge[last], pl->pair_run, pl->pair_groups)
                                     : PairRunEntry{nullptr, 0, 0};
         if (kg.fn) {

@@ -62,7 +62,7 @@ def test_single_stage_plan_needs_no_device():
     assert lib.rmx_plan_set_option(h, b"pair_run", 16) == 0 and lib.rmx_plan_set_option(h, b"pair_prefetch", 0) == 0
     assert lib.rmx_plan_set_option(h, b"pair_run", 5) == -1 and lib.rmx_plan_set_option(h, b"no_such_knob", 1) == -1
     assert b"no_such_knob" in lib.rmx_last_error()
-    for knob, good, bad in ((b"pair_groups", (0, 2, 3), (1, 4)), (b"pair_ctas", (4, 5, 6), (3, 7)), (b"pair_store", (0, 1), ())):
+    for knob, good, bad in ((b"pair_groups", (0, 2, 3), (1, 4)), (b"pair_ctas", (4, 5, 6), (3, 7)), (b"pair_store", (0, 1, 2), (3,))):
         assert all(lib.rmx_plan_set_option(h, knob, v) == 0 for v in good), knob
         assert all(lib.rmx_plan_set_option(h, knob, v) == -1 for v in bad), knob
     assert lib.rmx_welch_path(h, None) == 0                                  # 16-point plan: no cluster kernel
