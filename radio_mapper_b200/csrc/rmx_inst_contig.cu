@@ -54,12 +54,20 @@ static PairRunEntry pair_run_entry() {
                         (PREFETCH || STAGED) ? exchange + size_t(GEO::N) * sizeof(float2) : GEO::SMEM_BYTES, RUN};
 }
 
-// run: pairs walked by one CTA (8 or 16); mem: 0 = per-thread loads and stores, 1 = next X_j row prefetched by a bulk
+template <int RUN>
+static PairRunEntry pair_run_xi_smem_entry() {
+    using GEO = TileGeom<12, 4, false>;
+    const size_t exchange = size_t((GEO::NP + 15) & ~15) * sizeof(float2);
+    return PairRunEntry{(PassKernel)k_contig_pair_run<12, 4, RUN, false, 0, RMX_PAIR_RUN_CTAS, true>, exchange + size_t(GEO::N) * sizeof(float2), RUN};
+}
+
+// run: pairs walked by one CTA (8 or 16); mem: 4 = X_i row in shared memory instead of registers (no prefetch); 0 = per-thread loads and stores, 1 = next X_j row prefetched by a bulk
 // copy into shared memory, 2 = finished row staged in shared memory and stored by a bulk copy, 3 = prefetch + the
 // finished row staged in the exchange buffer and stored by a bulk copy
 PairRunEntry get_pair_run_kernel(int logn, int loge, int run, int mem, int ctas) {
     if (logn == 11 && loge == 3) return get_pair_run_kernel8(run, mem == 1 || mem == 3 ? 1 : 0, ctas);
     if (logn == 12 && loge == 4) {
+        if (mem == 4) return run >= 16 ? pair_run_xi_smem_entry<16>() : pair_run_xi_smem_entry<8>();
         if (run >= 16) return mem == 1 ? pair_run_entry<16, true, 0>() : mem == 2 ? pair_run_entry<16, false, 1>() : mem == 3 ? pair_run_entry<16, true, 2>() : pair_run_entry<16, false, 0>();
         return mem == 1 ? pair_run_entry<8, true, 0>() : mem == 2 ? pair_run_entry<8, false, 1>() : mem == 3 ? pair_run_entry<8, true, 2>() : pair_run_entry<8, false, 0>();
     }

@@ -736,8 +736,11 @@ __global__ void __launch_bounds__(kThreads, min_ctas(LOGE)) k_col_fwd_cu8_tma(co
 // stores per thread through the LSU queue that the next pair's shared-memory exchanges share.
 // STAGED == 2 (with PREFETCH): the finished row is staged in the EXCHANGE buffer (free between the last gather of a
 // pair and the first scatter of the next) and leaves by one bulk copy; the landing buffer keeps prefetching.
-template <int LOGN, int LOGE, int RUN, bool PREFETCH, int STAGED = 0, int CTAS = RMX_PAIR_RUN_CTAS>
+// XI_SMEM (without PREFETCH / STAGED; the same 32 KB buffer): the stationary X_i row lives in shared memory, each thread
+// re-reading exactly the 16 values it wrote (no barrier), instead of in 32 registers next to the tile.
+template <int LOGN, int LOGE, int RUN, bool PREFETCH, int STAGED = 0, int CTAS = RMX_PAIR_RUN_CTAS, bool XI_SMEM = false>
 __global__ void __launch_bounds__(kThreads, CTAS) k_contig_pair_run(const PassParams p) {
+    static_assert(!XI_SMEM || (!PREFETCH && STAGED == 0), "one 32 KB buffer: landing zone, store staging or the X_i row");
     static_assert(!(PREFETCH && STAGED == 1), "one 32 KB buffer: landing zone or store staging");
     static_assert(STAGED != 2 || (PREFETCH && RMX_PAIR_SPLIT), "exchange-buffer staging rides on the prefetch path's barriers");
     using GEO = TileGeom<LOGN, LOGE, false>;
@@ -786,8 +789,13 @@ __global__ void __launch_bounds__(kThreads, CTAS) k_contig_pair_run(const PassPa
         const int2 pr = __ldg(p.pairs + pidx);
         if (pr.x != cur_i) {                                  // CTA-uniform
             const float2* __restrict__ xi = p.spectra + ((long long)pr.x << p.logL) + (row << LOGN);
+            if constexpr (XI_SMEM) {
 #pragma unroll
-            for (int u = 0; u < E; ++u) a[u] = RMX_X_LOAD(xi + i0 + u * NT);
+                for (int u = 0; u < E; ++u) land[i0 + u * NT] = RMX_X_LOAD(xi + i0 + u * NT);
+            } else {
+#pragma unroll
+                for (int u = 0; u < E; ++u) a[u] = RMX_X_LOAD(xi + i0 + u * NT);
+            }
             cur_i = pr.x;
         }
         float2 r[E];
@@ -813,8 +821,15 @@ __global__ void __launch_bounds__(kThreads, CTAS) k_contig_pair_run(const PassPa
             for (int u = 0; u < E; ++u) r[u] = cmul_conj(make_float2((float)(pidx + u), (float)(i0 - u)), a[u]);
             (void)xj;
 #else
+            if constexpr (XI_SMEM) {
 #pragma unroll
-            for (int u = 0; u < E; ++u) r[u] = cmul_conj(RMX_X_LOAD(xj + i0 + u * NT), a[u]);     // X_j * conj(X_i)
+                for (int u = 0; u < E; ++u) r[u] = RMX_X_LOAD(xj + i0 + u * NT);
+#pragma unroll
+                for (int u = 0; u < E; ++u) r[u] = cmul_conj(r[u], land[i0 + u * NT]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < E; ++u) r[u] = cmul_conj(RMX_X_LOAD(xj + i0 + u * NT), a[u]);     // X_j * conj(X_i)
+            }
 #endif
 #if !RMX_PAIR_SPLIT
             if (pidx != first) {

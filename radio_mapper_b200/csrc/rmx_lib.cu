@@ -80,6 +80,7 @@ struct rmx_plan {
     int pair_prefetch = 1;            // next X_j row by bulk copy into shared memory
     int pair_ctas = 5;                // resident CTAs per SM the 2048-point row pass (RMX_PLAN_ROW_E8) is compiled for: 4 | 5 | 6
     int pair_groups = 0;              // 2 | 3: warp groups per CTA handing the FP32 pipe round (rmx_pair_pp.cuh); 0 = independent CTAs
+    int pair_xi_smem = 0;             // stationary X_i row in shared memory instead of registers (takes the prefetch buffer's place)
     int pair_store = 0;               // finished rows through a staging buffer + bulk copy (takes the prefetch buffer's place)
     long long fwd_group_bytes = 0;    // forward passes run over groups of signals whose spectra fit this many bytes (0 = all at once)
     int welch_clusters = 0;           // resident clusters of the Welch kernel (0 = occupancy query)
@@ -297,6 +298,7 @@ extern "C" int rmx_plan_set_option(rmx_plan* pl, const char* name, long long val
     if (!pl || !name) return fail(RMX_ERR_ARG, "null argument to rmx_plan_set_option");
     if (!strcmp(name, "pair_run")) { if (value != 8 && value != 16) return fail(RMX_ERR_ARG, "pair_run must be 8 or 16"); pl->pair_run = (int)value; }
     else if (!strcmp(name, "pair_prefetch")) pl->pair_prefetch = value != 0;
+    else if (!strcmp(name, "pair_xi_smem")) pl->pair_xi_smem = value != 0;
     else if (!strcmp(name, "pair_store")) {
         if (value < 0 || value > 2) return fail(RMX_ERR_ARG, "pair_store must be 0, 1 or 2 (got %lld)", (long long)value);
         pl->pair_store = (int)value;
@@ -534,11 +536,11 @@ static int launch_pair_pass(const rmx_plan* pl, const PassParams& pp, int cnt, c
     const bool dst_ok = (reinterpret_cast<uintptr_t>(pp.dst) & 15) == 0;
     const bool staged = pl->pair_store == 1 && dst_ok;                       // dedicated staging buffer, no prefetch
     const bool xstaged = pl->pair_store == 2 && dst_ok && prefetch;           // staged in the exchange buffer, with prefetch
-    const PairRunEntry kr = get_pair_run_kernel(pl->logn[last], pl->loge[last], pl->pair_run, xstaged ? 3 : staged ? 2 : prefetch ? 1 : 0, pl->pair_ctas);
+    const PairRunEntry kr = get_pair_run_kernel(pl->logn[last], pl->loge[last], pl->pair_run, pl->pair_xi_smem ? 4 : xstaged ? 3 : staged ? 2 : prefetch ? 1 : 0, pl->pair_ctas);
     if (kr.fn && pl->n_passes >= 2 && !(pl->flags & RMX_PLAN_NO_PAIR_RUN)) {
         const long long rows = 1LL << (pl->logL - pl->logn[last]);
         const long long blocks = (cnt + kr.run - 1) / kr.run;
-        const PairRunEntry kg = (pl->pair_groups && prefetch && !staged && !xstaged)
+        const PairRunEntry kg = (pl->pair_groups && prefetch && !staged && !xstaged && !pl->pair_xi_smem)
                                     ? get_pair_run_pp_kernel(pl->logn[last], pl->loge[last], pl->pair_run, pl->pair_groups)
                                     : PairRunEntry{nullptr, 0, 0};
         if (kg.fn) {
