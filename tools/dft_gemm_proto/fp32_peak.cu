@@ -63,8 +63,12 @@ int main(int argc, char** argv) {
     const char* names[3] = {"ffma", "ffma2", "fadd"};
     const double flop_per_lane_instr[3] = {2.0, 4.0, 1.0};
     const double lane_instr_per_iter[3] = {128.0, 64.0, 128.0};
+    // optional 2nd / 3rd argument: only this stream (0 ffma, 1 ffma2, 2 fadd) / only this many CTAs per SM -- for runs long
+    // enough to sit at the board power limit
+    const int only_mode = argc > 2 ? atoi(argv[2]) : -1, only_k = argc > 3 ? atoi(argv[3]) : -1;
     for (int mode = 0; mode < 3; ++mode)
         for (int k : {1, 2, 3, 4, 6, 8}) {
+            if ((only_mode >= 0 && mode != only_mode) || (only_k >= 0 && k != only_k)) continue;
             const int grid = k * sms;
             cudaEvent_t e0, e1;
             cudaEventCreate(&e0); cudaEventCreate(&e1);
