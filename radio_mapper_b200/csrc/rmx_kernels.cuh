@@ -105,6 +105,7 @@ struct PassParams {
     int post_logn;            // C_INV_PAIR: log2 of that pass's transform length (row index = row mod n)
     float post_scale;         // C_INV_PAIR: scale folded into those twiddles (a power of two)
     int prefetch;             // C_FWD_PSD: next segment's row by bulk copy into a landing buffer behind the exchange area
+    int xi_early;             // k_contig_pair_run: a new X_i row is loaded one pair ahead (right after the pair product that last used the old one)
 };
 
 enum ContigMode { C_FWD = 0, C_FWD_CU8 = 1, C_INV_PAIR = 2, C_FWD_PSD = 3, C_INV_PAIR_WIN2 = 4, C_INV_PAIR_WIN4 = 5, C_INV_PAIR_WIN8 = 6 };
@@ -808,11 +809,21 @@ __global__ void __launch_bounds__(kThreads, CTAS) k_contig_pair_run(const PassPa
                 if (threadIdx.x == 0 && pidx != first) bulk_store_wait_read();      // previous row has left the exchange buffer
             }
             __syncthreads();          // landing buffer consumed; also: everyone is past the previous pair's last exchange read
-            if (threadIdx.x == 0 && pidx + 1 < last) {
+            if (pidx + 1 < last) {
                 const int2 prn = __ldg(p.pairs + pidx + 1);
-                fence_proxy_async();
-                mbar_expect_tx(&mbar, ROW_BYTES);
-                bulk_load_1d(land, p.spectra + ((long long)prn.y << p.logL) + (row << LOGN), ROW_BYTES, &mbar);
+                if (threadIdx.x == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(&mbar, ROW_BYTES);
+                    bulk_load_1d(land, p.spectra + ((long long)prn.y << p.logL) + (row << LOGN), ROW_BYTES, &mbar);
+                }
+                // the next pair starts a new X_i row: its loads go out now -- the registers are free until the next pair
+                // product -- and arrive during this pair's transform instead of stalling the next pair
+                if (p.xi_early && prn.x != cur_i) {
+                    const float2* __restrict__ xi = p.spectra + ((long long)prn.x << p.logL) + (row << LOGN);
+#pragma unroll
+                    for (int u = 0; u < E; ++u) a[u] = RMX_X_LOAD(xi + i0 + u * NT);
+                    cur_i = prn.x;
+                }
             }
         } else {
             const float2* __restrict__ xj = p.spectra + ((long long)pr.y << p.logL) + (row << LOGN);

@@ -80,6 +80,7 @@ struct rmx_plan {
     int pair_prefetch = 1;            // next X_j row by bulk copy into shared memory
     int pair_ctas = 5;                // resident CTAs per SM the 2048-point row pass (RMX_PLAN_ROW_E8) is compiled for: 4 | 5 | 6
     int pair_groups = 0;              // 2 | 3: warp groups per CTA handing the FP32 pipe round (rmx_pair_pp.cuh); 0 = independent CTAs
+    int pair_xi_early = 1;            // a new X_i row is loaded one pair ahead of its first use (prefetch path)
     int pair_xi_smem = 0;             // stationary X_i row in shared memory instead of registers (takes the prefetch buffer's place)
     int pair_store = 0;               // finished rows through a staging buffer + bulk copy (takes the prefetch buffer's place)
     long long fwd_group_bytes = 0;    // forward passes run over groups of signals whose spectra fit this many bytes (0 = all at once)
@@ -299,6 +300,7 @@ extern "C" int rmx_plan_set_option(rmx_plan* pl, const char* name, long long val
     if (!strcmp(name, "pair_run")) { if (value != 8 && value != 16) return fail(RMX_ERR_ARG, "pair_run must be 8 or 16"); pl->pair_run = (int)value; }
     else if (!strcmp(name, "pair_prefetch")) pl->pair_prefetch = value != 0;
     else if (!strcmp(name, "pair_xi_smem")) pl->pair_xi_smem = value != 0;
+    else if (!strcmp(name, "pair_xi_early")) pl->pair_xi_early = value != 0;
     else if (!strcmp(name, "pair_store")) {
         if (value < 0 || value > 2) return fail(RMX_ERR_ARG, "pair_store must be 0, 1 or 2 (got %lld)", (long long)value);
         pl->pair_store = (int)value;
@@ -529,7 +531,9 @@ static int launch_fwd_tma(const rmx_plan* pl, const PassParams& pp, int cnt, cud
 }
 
 // innermost inverse pass over `cnt` pairs
-static int launch_pair_pass(const rmx_plan* pl, const PassParams& pp, int cnt, cudaStream_t st) {
+static int launch_pair_pass(const rmx_plan* pl, const PassParams& pp_in, int cnt, cudaStream_t st) {
+    PassParams pp = pp_in;
+    pp.xi_early = pl->pair_xi_early;
     const int last = pl->n_passes - 1;
     // the bulk-copy prefetch needs 16-byte aligned spectrum rows (rows are multiples of 32 KB apart)
     const bool prefetch = pl->pair_prefetch != 0 && (reinterpret_cast<uintptr_t>(pp.spectra) & 15) == 0;

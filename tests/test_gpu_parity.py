@@ -198,7 +198,7 @@ def test_kernel_variants_agree(rmx, log_n):
     for name, flags, options in [("default", 0, {}), ("no_tma", nat.PLAN_NO_TMA, {}), ("no_pair_run", nat.PLAN_NO_PAIR_RUN, {}),
                                  ("twiddle_in_col", nat.PLAN_TWIDDLE_IN_COL, {}),
                                  ("no_prefetch", 0, {"pair_prefetch": 0}), ("run16", 0, {"pair_run": 16}),
-                                 ("staged_store", 0, {"pair_store": 1}), ("xstaged_store", 0, {"pair_store": 2}), ("xi_smem", 0, {"pair_xi_smem": 1}),
+                                 ("staged_store", 0, {"pair_store": 1}), ("xstaged_store", 0, {"pair_store": 2}), ("xi_smem", 0, {"pair_xi_smem": 1}), ("xi_late", 0, {"pair_xi_early": 0}),
                                  ("groups2", 0, {"pair_groups": 2}), ("groups3", 0, {"pair_groups": 3}),
                                  ("row_e8", nat.PLAN_ROW_E8, {}), ("row_e8_ctas4", nat.PLAN_ROW_E8, {"pair_ctas": 4, "pair_prefetch": 0}),
                                  ("fwd_groups", 0, {"fwd_group_bytes": 3 * 8 * 2 * n}), ("fwd_ldg", 0, {"fwd_tma": 0}),
@@ -214,7 +214,7 @@ def test_kernel_variants_agree(rmx, log_n):
     # the TMA-fed forward pass (default) and the per-thread 128-bit staging stage the same bytes differently:
     # identical spectra, hence identical records
     assert np.array_equal(results["fwd_ldg"], ref) and np.array_equal(results["fwd_ldg_full"], results["default_full"])
-    for name in ("no_tma", "no_pair_run", "twiddle_in_col", "no_prefetch", "run16", "staged_store", "xstaged_store", "xi_smem", "groups2", "groups3", "row_e8", "row_e8_ctas4", "fwd_groups", "fwd_ldg", "all_off"):
+    for name in ("no_tma", "no_pair_run", "twiddle_in_col", "no_prefetch", "run16", "staged_store", "xstaged_store", "xi_smem", "xi_late", "groups2", "groups3", "row_e8", "row_e8_ctas4", "fwd_groups", "fwd_ldg", "all_off"):
         _check_records(results[name], ref)
         a, b = results[name + "_full"], results["default_full"]
         assert np.linalg.norm(a - b) <= 2e-6 * np.linalg.norm(b), name
