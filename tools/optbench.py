@@ -1,7 +1,10 @@
 #!/usr/bin/env python3
 """A/B of plan options / flags in ONE process (developer aid): per-kernel ms per window for each setting.
 
-    python tools/optbench.py BUOYS LOG2_SAMPLES ITERS 'name=value,...;name=value,...;...'
+    python tools/optbench.py BUOYS LOG2_SAMPLES ITERS 'name=value,...;name=value,...;...' [IDLE_MS]
+
+IDLE_MS > 0 synchronises and sleeps that long between iterations (per-kernel times then show what the kernels do
+on a GPU that is not at its power limit; ms_per_window_total includes the sleeps and is meaningless).
 
 Each ';'-separated setting is a comma list of plan options (rmx_plan_set_option) and/or `flags=<int>`; an empty
 setting is the default plan.  Prints one JSON line per setting."""
@@ -15,6 +18,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 N = 1 << (int(sys.argv[2]) if len(sys.argv) > 2 else 22)
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 settings = [x.strip() for x in (sys.argv[4] if len(sys.argv) > 4 else "").split(";")]
+idle_ms = float(sys.argv[5]) if len(sys.argv) > 5 else 0.0
 iq, delays = synth.delayed_buoys_torch(7, B, 1, N, torch.device("cuda"))
 pairs_h = engine.pair_table(B)
 pairs = torch.from_numpy(pairs_h).cuda()
@@ -42,12 +46,16 @@ for setting in settings:
     for _ in range(iters):
         S = plan.forward(iq[:, 0, :])
         rec = plan.xcorr_pairs_peak(S, pairs)
+        if idle_ms > 0:
+            torch.cuda.synchronize()
+            import time
+            time.sleep(idle_ms * 1e-3)
     e1.record()
     torch.cuda.synchronize()
     prof = plan.profile_collect()
     plan.profile(False)
     per = {k: round(v[1] / iters, 4) for k, v in prof.items()}
-    print(json.dumps({"setting": setting or "default", "B": B, "N": N, "passes": plan.pass_lengths,
+    print(json.dumps({"setting": setting or "default", "idle_ms_between_iterations": idle_ms, "B": B, "N": N, "passes": plan.pass_lengths,
                       "lags_ok": bool(np.array_equal(got["lag"], want)),
                       "peak_maxrel_vs_first": float(np.max(np.abs(got["peak"] / ref["peak"] - 1))),
                       "ms_per_window_total": round(e0.elapsed_time(e1) / iters, 4), "ms_per_kernel": per}), flush=True)
