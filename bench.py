@@ -110,7 +110,8 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        # a timed region of a few ms (cfg1) can end before nvidia-smi has printed its first sample
+        time.sleep(0.12 if (self.t1 or 0) - (self.t0 or 0) > 0.2 else 0.6)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
