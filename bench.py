@@ -265,7 +265,7 @@ def run_reference(args, wl):
                          "host_cpus": cores},
         "e2e": {"value": ps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def welch_roofline(n_seg, nperseg, ms, clocks):
@@ -683,9 +683,29 @@ def run_b200(args, wl):
         "windowed_search": windowed,
         "welch_psd": welch, "block_detect": detect, "pair_sharded": pair_sharded,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_FD = None
+
+
+def _keep_stdout_for_the_result():
+    """stdout carries ONE JSON line.  Libraries write there too (NCCL prints its version line to fd 1 when the first
+    communicator comes up), so everything but the result goes to stderr: fd 1 is parked and points at stderr until
+    _emit() prints the line."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    if _RESULT_FD is not None:
+        os.dup2(_RESULT_FD, 1)
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -696,6 +716,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("RMX_WORKLOAD", "cfg3"), choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    _keep_stdout_for_the_result()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
