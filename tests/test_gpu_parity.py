@@ -134,6 +134,31 @@ def test_xcorr_chunked_workspace_and_pair_subsets(rmx):
     assert plan.xcorr_pairs_peak(S, torch.empty((0, 2), dtype=torch.int32, device="cuda")).shape[0] == 0
 
 
+@pytest.mark.parametrize("options", [{}, {"pair_prefetch": 0}, {"pair_run": 16}, {"pair_groups": 2}, {"pair_store": 2}])
+def test_xcorr_arbitrary_pair_lists(rmx, options):
+    """The X_i-stationary row pass walks runs of consecutive pairs and re-reads X_i when i changes: any pair list must
+    do -- shuffled, reversed (j, i), repeated and auto-correlation (i, i) entries, lengths that are no multiple of the
+    run -- with records bit-identical to the same pairs taken from the ordered table (two-pass plan 64 x 4096)."""
+    n, b = 1 << 17, 7
+    iq, delays, _ = synth.delayed_buoys(4242, b, n, max_delay=300)
+    plan = rmx.Plan(b, n, options=options)
+    S = plan.forward(_cuda(iq))
+    table = rmx.pair_table(b)
+    ordered = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, _cuda(table))).copy()
+    assert list(ordered["lag"]) == [delays[j] - delays[i] for i, j in oracle.pair_list(b)]
+    rng = np.random.default_rng(5)
+    sel = rng.permutation(len(table))[:17]                       # 17 pairs: two full runs of 8 and one of 1
+    got = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, _cuda(table[sel].copy())))
+    assert got.tobytes() == ordered[sel].tobytes()
+    mixed = np.concatenate([table[sel[:5]], table[sel[:5], ::-1], np.array([[3, 3], [0, 0], [6, 6]], dtype=table.dtype),
+                            table[sel[:3]]]).astype(np.int32)
+    got = rmx.peaks_to_numpy(plan.xcorr_pairs_peak(S, _cuda(mixed)))
+    assert got[:5].tobytes() == ordered[sel[:5]].tobytes() and got[13:].tobytes() == ordered[sel[:3]].tobytes()
+    assert np.array_equal(got["lag"][5:10], -ordered["lag"][sel[:5]])           # (j, i): mirrored correlation
+    assert np.allclose(got["peak"][5:10], ordered["peak"][sel[:5]], rtol=1e-6)
+    assert np.array_equal(got["lag"][10:13], [0, 0, 0]) and np.all(np.abs(got["frac"][10:13]) < 1e-3)   # auto-correlation
+
+
 @pytest.mark.parametrize("max_lag", [0, 5, 342, 5000])
 def test_xcorr_max_lag_window(rmx, max_lag):
     iq, delays, _ = synth.delayed_buoys(31, 4, 1 << 14, max_delay=300)
