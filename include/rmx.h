@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RMX_VERSION 200
+#define RMX_VERSION 201
 
 #if defined(__GNUC__)
 #define RMX_API __attribute__((visibility("default")))

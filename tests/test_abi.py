@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), name
     assert sorted(_native.SIGNATURES) == names        # the ctypes table covers the header, no more, no less
-    assert lib.rmx_version() == 200
+    assert lib.rmx_version() == 201
 
 
 def test_header_cites_reference_lines():
