@@ -134,6 +134,23 @@ def test_xcorr_chunked_workspace_and_pair_subsets(rmx):
     assert plan.xcorr_pairs_peak(S, torch.empty((0, 2), dtype=torch.int32, device="cuda")).shape[0] == 0
 
 
+def test_correlate_chain_is_deterministic(rmx):
+    """No atomics on the data path of the correlate stage: the same window must give bit-identical spectra and peak
+    records every time; a difference would be a race (mbarrier phases, bulk-copy ordering, exchange-buffer reuse).
+    tools/soak.py runs the same check at the BASELINE sizes (profiles/r02_soak_determinism.jsonl)."""
+    import torch
+    for n, b in ((1 << 17, 12), (1 << 19, 5)):
+        iq, _, _ = synth.delayed_buoys(31 + b, b, n, max_delay=200)
+        plan = rmx.Plan(b, n)
+        dev, pairs = _cuda(iq), _cuda(rmx.pair_table(b))
+        first_s = plan.forward(dev).clone()
+        first = plan.xcorr_pairs_peak(first_s, pairs).clone()
+        for _ in range(150):
+            s = plan.forward(dev)
+            assert torch.equal(torch.view_as_real(s), torch.view_as_real(first_s))
+            assert torch.equal(plan.xcorr_pairs_peak(s, pairs), first)
+
+
 @pytest.mark.parametrize("options", [{}, {"pair_prefetch": 0}, {"pair_run": 16}, {"pair_groups": 2}, {"pair_store": 2}])
 def test_xcorr_arbitrary_pair_lists(rmx, options):
     """The X_i-stationary row pass walks runs of consecutive pairs and re-reads X_i when i changes: any pair list must
